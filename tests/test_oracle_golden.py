@@ -1,0 +1,169 @@
+"""Pins the CPU oracle (oracle/) against the golden vectors held by the
+reference's own tests (tests/golden/reference_kats.json, transcribed by
+tests/golden/make_golden.py with file:line citations).  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+RTOL = 1e-8   # the reference tests use `≈` (rtol = sqrt(eps) ~ 1.5e-8); we hold the oracle tighter
+
+
+def _op(e, dtype=np.float64):
+    dx = e["dx"] if np.ndim(e["dx"]) == 0 else np.asarray(e["dx"])
+    if e["kind"] == "centered":
+        return O.CenteredDifference(e["d"], e["a"], dx, e["n"], e["coeff"], dtype=dtype)
+    return O.UpwindDifference(e["d"], e["a"], dx, e["n"], e["coeff"], offside=e.get("offside", 0), dtype=dtype)
+
+
+def test_operator_matrices(golden):
+    assert len(golden["operator_matrices"]) >= 30
+    for e in golden["operator_matrices"]:
+        L = _op(e)
+        got = L.to_matrix()
+        want = np.asarray(e["matrix"])
+        if "rows" in e:
+            got = got[e["rows"][0]:e["rows"][1]]
+        scale = np.abs(want).max()
+        assert got.shape == want.shape, e["cite"]
+        assert np.abs(got - want).max() <= RTOL * scale, e["cite"]
+
+
+def test_bpv_equals_plain_on_fixtures(golden):
+    """convolutions.jl(test):45-81: DerivativeOperator*BoundaryPaddedVector == stencil*[l;u;r]."""
+    rng = np.random.default_rng(1)
+    for e in golden["operator_matrices"]:
+        L = _op(e)
+        n = e["n"]
+        l, r = rng.random(2)
+        u = rng.random(n)
+        want = L.to_matrix() @ np.concatenate([[l], u, [r]])
+        got = L.mul1d_bpv(l, r, u)
+        assert np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max()), e["cite"]
+
+
+def test_interior_weights(golden):
+    g = golden["interior_weights"]
+    for e in g["centered"]:
+        L = O.CenteredDifference(e["d"], e["a"], 1.0, 12)
+        assert np.allclose(L.stencil_coefs, e["w"], atol=1e-10, rtol=0)
+    for e in g["upwind"]:
+        L = O.UpwindDifference(e["d"], e["a"], 1.0, 12)
+        assert np.allclose(L.stencil_coefs, e["w"], atol=1e-10, rtol=0)
+
+
+def test_vector_coefficients(golden):
+    g = golden["vector_coefficients"]
+    x = np.asarray(g["x"]); c = np.asarray(g["c"])
+    A = O.CenteredDifference(2, 2, 1.0, 3)
+    B = O.UpwindDifference(1, 1, 1.0, 3, 1.0)
+    Cc = O.UpwindDifference(1, 1, 1.0, 3, [2.0, 3.0, 4.0])
+    for mk in (lambda: O.CenteredDifference(2, 2, 1.0, 3), lambda: O.UpwindDifference(1, 1, 1.0, 3, 1.0),
+               lambda: O.UpwindDifference(1, 1, 1.0, 3, [2.0, 3.0, 4.0])):
+        base = mk(); scaled = mk().scale(c)
+        assert np.allclose(base.mul1d_plain(x) * c, scaled.mul1d_plain(x), rtol=1e-12)
+    assert np.array_equal(A.scale(c).coefficients, c)
+    assert np.array_equal(B.scale(c).coefficients, c)
+    assert np.array_equal(Cc.scale(c).coefficients, g["cC_coefficients"])
+
+
+def test_robin_order1_closed_forms(golden):
+    for case in golden["robin_order1"]["cases"]:
+        al, bl, cl, dx, ar, br, cr = (case[k] for k in ("al", "bl", "cl", "dx", "ar", "br", "cr"))
+        u = np.asarray(case["u"])
+        want_l = (cl - (bl / dx) * u[0]) / (al - bl / dx)
+        want_r = (cr + (br / dx) * u[-1]) / (ar + br / dx)
+        for Q in (O.RobinBC((al, bl, cl), (ar, br, cr), dx),
+                  O.RobinBC((al, bl, cl), (ar, br, cr), dx * np.ones(len(u)))):
+            l, r = Q.ghosts(u)
+            assert np.isclose(l, want_l, rtol=1e-10) and np.isclose(r, want_r, rtol=1e-10)
+            # Q_L first/last row and Q_b (robin.jl:21-26)
+            assert np.isclose(Q.a_l[0], 1 / (1 - al * dx / bl), rtol=1e-10)
+            assert np.isclose(Q.a_r[0], 1 / (1 + ar * dx / br), rtol=1e-10)
+            assert np.isclose(Q.b_l[0], cl / (al - bl / dx), rtol=1e-10)
+            assert np.isclose(Q.b_r[0], cr / (ar + br / dx), rtol=1e-10)
+
+
+def test_robin_order3_and_general(golden):
+    g = golden["robin_order3"]
+    u = np.asarray(g["u"])
+    Q = O.RobinBC(g["l"], g["r"], g["dx"], g["order"])
+    l, r = Q.ghosts(u)
+    assert np.isclose(l, g["u0"], rtol=1e-12) and np.isclose(r, g["uend"], rtol=1e-12)
+    for dx in (1.0, np.ones(10)):
+        G = O.GeneralBC(g["general_alpha"], g["general_alpha"], dx, 3)
+        l, r = G.ghosts(u)
+        assert np.isclose(l, g["u0"], rtol=1e-12) and np.isclose(r, g["uend"], rtol=1e-12)
+
+
+def test_dirichlet_neumann_special_cases():
+    # bc_operators.jl:173-183; Dirichlet relies on 1/0 = Inf giving a = (-0.0, 0.0), b = gamma
+    D = O.DirichletBC(2.5, -1.5)
+    assert np.all(D.a_l == 0) and np.all(D.a_r == 0) and D.b_l[0] == 2.5 and D.b_r[0] == -1.5
+    N = O.NeumannBC((0.3, -0.2), 0.1, 1)
+    assert N.a_l[0] == 1 and N.a_r[0] == 1
+    assert np.isclose(N.b_l[0], -0.3 * 0.1) and np.isclose(N.b_r[0], -0.2 * 0.1)
+
+
+def _bc_from(spec, dx):
+    if spec["type"] == "neumann0":
+        return O.Neumann0BC(dx, spec["order"])
+    return O.RobinBC(spec["l"], spec["r"], dx, spec["order"])
+
+
+def test_ghost_operator_matrices(golden):
+    """Array(L*Q)[1] fixtures of BasicSDOExamples.jl: linear part of u -> L*(Q*u), recovered by probing."""
+    g = golden["ghost_operator_matrices"]
+    dx, M = g["dx"], g["M"]
+    for case in g["cases"]:
+        Q = _bc_from(case["bc"], dx)
+        total = np.zeros((M, M))
+        for t in case["terms"]:
+            mk = O.CenteredDifference if t["kind"] == "centered" else O.UpwindDifference
+            L = mk(t["d"], t["a"], dx, M, t["coeff"])
+            if "scale" in t:
+                L.scale(t["scale"])
+            affine = O.apply_axis(L, np.zeros(M), Q)
+            lin = np.stack([O.apply_axis(L, e, Q) - affine for e in np.eye(M)], axis=1)
+            total += lin
+        total *= case.get("scale", 1.0)
+        want = np.asarray(case["matrix"])
+        assert np.abs(total - want).max() <= 1e-9 * np.abs(want).max() + 1e-12, case["name"]
+
+
+def test_nd_axis(golden):
+    from tests.golden.make_golden import fourth_deriv_approx_stencil, second_derivative_stencil
+    for case in golden["nd_axis"]["cases"]:
+        shape, ax, n = case["shape"], case["axis"], case["n"]
+        idx = np.arange(1, shape[ax - 1] + 1) * 0.1
+        line = np.sin(idx) if case["field"] == "sin" else np.cos(idx)
+        bshape = [1] * len(shape); bshape[ax - 1] = -1
+        M = np.broadcast_to(line.reshape(bshape), shape).copy(order="F")
+        L = O.CenteredDifference(case["d"], case["a"], case["dx"], n, axis=ax)
+        got = O.apply_axis(L, M)
+        S = fourth_deriv_approx_stencil(n) if case["d"] == 4 else second_derivative_stencil(n)
+        correct = (1.0 / case["dx"] ** case["d"]) * (S @ line)
+        want = np.broadcast_to(correct.reshape(bshape), got.shape)
+        assert got.shape == tuple(s - 2 if i == ax - 1 else s for i, s in enumerate(shape))
+        assert np.allclose(got, want, rtol=1e-7, atol=1e-7 * np.abs(correct).max())
+
+
+def test_fornberg_f32_is_f32_arithmetic():
+    w32 = O.calculate_weights(2, 0.0, np.arange(-3, 4), dtype=np.float32)
+    w64 = O.calculate_weights(2, 0.0, np.arange(-3, 4), dtype=np.float64)
+    assert w32.dtype == np.float32
+    assert np.allclose(w32, w64, rtol=1e-6)
+    # sum-to-zero fix (fornberg.jl:57-61)
+    assert abs(w64.sum()) <= 1e-15
+    # (1,4): centre weight is the negated residual, not exactly 0
+    w = O.calculate_weights(1, 0.0, np.arange(-2, 3))
+    assert abs(w[2]) < 1e-15
+
+
+def test_julia_cumsum_is_cumsum_to_rounding():
+    # Base.cumsum is accumulate_pairwise!: c[i] = v1 + (v2 + ... + vi), pairwise above 128 elements;
+    # equal to the sequential sum up to rounding only.
+    for n in (3, 100, 1000):
+        v = np.random.default_rng(0).random(n)
+        assert np.allclose(O.julia_cumsum(v), np.cumsum(v), rtol=1e-13)
+    assert np.array_equal(O.julia_cumsum(np.array([1.0, 2.0, 3.0])), [1.0, 3.0, 6.0])
