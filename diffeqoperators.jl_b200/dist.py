@@ -1,0 +1,109 @@
+"""Slab-decomposed application: one process per GPU, the last axis split into contiguous slabs, halo
+planes exchanged by the library (NCCL send/recv over NVLink) overlapped with the interior planes.
+
+Host-side responsibilities (this file): moving the 128-byte NCCL unique id between the ranks with
+whatever process group the host runtime has (torch.distributed here; MPI / Distributed.jl in a Julia
+deployment), slab bookkeeping, scatter/gather of host arrays.  No arithmetic happens here."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .apply import Plan, _bc_for_axis, _terms
+from .device import DeviceArray
+
+
+def slab_bounds(n_last: int, nranks: int, rank: int):
+    """[start, start+count) of `rank`'s planes along the last axis (same rule as deo_dist_slab;
+    the library call is the authority, this wrapper only marshals)."""
+    s = C.c_int64(0)
+    c = C.c_int64(0)
+    _lib.check(_lib.load().deo_dist_slab(int(n_last), int(nranks), int(rank), C.byref(s), C.byref(c)))
+    return int(s.value), int(c.value)
+
+
+def extended_slab(u_global: np.ndarray, rank: int, nranks: int, halo: int, fill=np.nan):
+    """Host helper (tests, scatter): the [halo | own planes | halo] block of `rank`, halos filled from the
+    neighbouring slabs where they exist and with `fill` at the physical faces (never read there)."""
+    n = u_global.shape[-1]
+    s, c = slab_bounds(n, nranks, rank)
+    ext = np.full(u_global.shape[:-1] + (c + 2 * halo,), fill, dtype=u_global.dtype, order="F")
+    lo, hi = max(s - halo, 0), min(s + c + halo, n)
+    ext[..., lo - (s - halo):hi - (s - halo)] = u_global[..., lo:hi]
+    return ext
+
+
+class SlabContext:
+    """Owns the library's NCCL communicator for this rank."""
+
+    def __init__(self, rank: int, nranks: int, id_bytes: bytes):
+        self.rank, self.nranks = int(rank), int(nranks)
+        h = C.c_void_p()
+        buf = C.create_string_buffer(bytes(id_bytes), _lib.DEO_DIST_ID_BYTES)
+        _lib.check(_lib.load().deo_dist_init(buf, self.rank, self.nranks, C.byref(h)))
+        self._h = h
+
+    @staticmethod
+    def new_unique_id() -> bytes:
+        buf = C.create_string_buffer(_lib.DEO_DIST_ID_BYTES)
+        _lib.check(_lib.load().deo_dist_unique_id(buf))
+        return buf.raw
+
+    @classmethod
+    def from_torch_distributed(cls, device: int | None = None):
+        """Bootstraps over an initialised torch.distributed process group (any backend): rank 0 creates
+        the NCCL unique id and broadcasts its bytes."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        if device is not None:
+            _lib.check(_lib.load().deo_init(int(device)))
+        backend = dist.get_backend()
+        dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+        t = torch.zeros(_lib.DEO_DIST_ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(cls.new_unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, src=0)
+        return cls(rank, world, bytes(t.cpu().numpy().tobytes()))
+
+    def __del__(self):
+        try:
+            if self._h is not None:
+                _lib.load().deo_dist_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+class SlabPlan(Plan):
+    """A fused operator application on this rank's slab of a global 3-D problem."""
+
+    def __init__(self, A, global_shape, dtype, ctx: SlabContext | None = None, local_rank=None, flags=0):
+        terms = _terms(A)
+        nd = len(global_shape)
+        bcs = []
+        for ax in range(1, nd + 1):
+            qs = [Q for L, Q in terms if L.axis == ax]
+            bcs.append(_bc_for_axis(qs[0], ax, nd) if qs else None)
+        super().__init__([(L, L.axis - 1) for L, _ in terms], bcs, tuple(global_shape), [False] * nd, dtype,
+                         flags=flags, dist=ctx._h if ctx is not None else None,
+                         local_rank=None if ctx is not None else local_rank)
+        self.ctx = ctx
+        rank, nranks = (ctx.rank, ctx.nranks) if ctx is not None else local_rank
+        self.start, self.count = slab_bounds(global_shape[-1], nranks, rank)
+        h = C.c_int32(0)
+        _lib.check(_lib.load().deo_dist_plan_halo(self._h, C.byref(h)))
+        self.halo = int(h.value)
+        self.global_shape = tuple(global_shape)
+        self.local_in_shape = tuple(global_shape[:-1]) + (self.count + 2 * self.halo,)
+        self.local_out_shape = tuple(global_shape[:-1]) + (self.count,)
+
+    def apply(self, du: DeviceArray, u_ext: DeviceArray):
+        _lib.check(_lib.load().deo_dist_plan_apply(self._h, du._h, u_ext._h))
+
+    def time(self, du: DeviceArray, u_ext: DeviceArray, reps: int) -> float:
+        ms = C.c_float(0)
+        _lib.check(_lib.load().deo_dist_plan_time(self._h, du._h, u_ext._h, reps, C.byref(ms)))
+        return float(ms.value)
