@@ -1,9 +1,192 @@
-// placeholder: the tiled kernel is added in a later step
-#include "common.hpp"
+// Host side of the tiled streaming kernel (kernel_star.cuh): eligibility, parameter packing, tensor map, dispatch.
+#include "kernel_star.cuh"
+
 namespace deo {
-int32_t star_configure(deo_plan*) { return DEO_OK; }
-int32_t launch_star(const deo_plan*, void*, const void*, long long, long long, cudaStream_t) {
-    set_error("star kernel not built");
+
+// ===================================== host side ==========================================================
+namespace {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+
+template <typename T>
+int32_t dispatch_T(const StarConfig& C, const void* u, void* du, long long z0, long long z1, cudaStream_t s) {
+    switch (C.R) {
+        case 1: return star_launch_R<T, 1>(C, u, du, z0, z1, s);
+        case 2: return star_launch_R<T, 2>(C, u, du, z0, z1, s);
+        case 3: return star_launch_R<T, 3>(C, u, du, z0, z1, s);
+        case 4: return star_launch_R<T, 4>(C, u, du, z0, z1, s);
+    }
+    set_error("star kernel: unsupported radius %d", C.R);
     return DEO_ERR_UNSUPPORTED;
 }
+
+template <typename T, int R>
+bool fill_params(const deo_plan* plan, const int kaxis_of_plan_axis[3], bool mid, StarConfig& C) {
+    using SP = StarParams<T, R>;
+    constexpr int NQ = SP::NQ, TB = SP::TB;
+    const DevPlan<T>& P = *reinterpret_cast<const DevPlan<T>*>(plan->devplan.data());
+    C.params.assign(sizeof(SP), 0);
+    SP& S = *reinterpret_cast<SP*>(C.params.data());
+    const int nd = plan->ndims;
+    const int march_plan_axis = nd - 1;
+    S.nx = P.n_out[0];
+    S.ny = mid ? P.n_out[1] : 1;
+    S.nz = P.n_out[march_plan_axis];
+    S.in_off_z = P.in_off[march_plan_axis];
+    S.row0_z = P.row0[march_plan_axis];
+    S.nglob_z = P.n_glob[march_plan_axis];
+    S.isy = mid ? P.in_stride[1] : 0;
+    S.osy = mid ? P.out_stride[1] : 0;
+    S.isz = P.in_stride[march_plan_axis];
+    S.osz = P.out_stride[march_plan_axis];
+    for (int a = 0; a < 3; ++a) { S.has[a] = 0; S.opidx[a] = -1; S.nlow[a] = S.nhigh[a] = 0; S.K_l[a] = S.K_r[a] = 0; }
+    // the explicit rows live in device memory: fetch them back through the host copies kept in the plan
+    for (int k = 0; k < P.nops; ++k) {
+        const DevOp<T>& op = P.ops[k];
+        const int ka = kaxis_of_plan_axis[op.axis];
+        if (ka < 0 || S.has[ka]) return false;
+        S.has[ka] = 1;
+        S.opidx[ka] = k;
+        const int r = -op.soff[0];
+        if (op.mode != MODE_CONST || op.ntaps != 2 * r + 1 || r < 1 || r > R) return false;
+        for (int t = 0; t < op.ntaps; ++t) S.w[ka][R - r + t] = op.w[0][t];
+        if (op.nlow > R || op.nhigh > R) return false;
+        S.nlow[ka] = op.nlow;
+        S.nhigh[ka] = op.nhigh;
+        const int n = op.n;
+        if (n < 4 * R + 4) return false;
+        std::vector<BRow<T>> br((size_t)op.nlow + op.nhigh);
+        if (!br.empty() && cudaMemcpy(br.data(), op.brows, br.size() * sizeof(BRow<T>), cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+        for (int i = 0; i < op.nlow; ++i) {
+            const BRow<T>& b = br[i];
+            if (b.start != 0 || b.ntaps > TB || b.acc64) return false;
+            for (int t = 0; t < b.ntaps; ++t) S.bw[ka][0][i][t] = b.w[t];
+        }
+        for (int i = 0; i < op.nhigh; ++i) {
+            const BRow<T>& b = br[(size_t)op.nlow + i];
+            if (b.start + b.ntaps != n + 2 || b.ntaps > TB || b.acc64) return false;
+            for (int t = 0; t < b.ntaps; ++t) S.bw[ka][1][i][TB - b.ntaps + t] = b.w[t];
+        }
+        // boundary condition of this axis
+        const HostBC& H = plan->bc[op.axis];
+        if (H.d.kind != DEO_BC_AFFINE || H.d.per_face) return false;
+        const int Kmax = ka == 2 ? NQ : kStarMaxK;
+        if (H.d.K_l > Kmax || H.d.K_r > Kmax || H.d.K_l > kStarMaxK || H.d.K_r > kStarMaxK) return false;
+        S.K_l[ka] = H.d.K_l;
+        S.K_r[ka] = H.d.K_r;
+        const T* al = (const T*)H.a_l.data();
+        const T* ar = (const T*)H.a_r.data();
+        for (int t = 0; t < H.d.K_l; ++t) S.a_l[ka][t] = al[t];
+        for (int t = 0; t < H.d.K_r; ++t) S.a_r[ka][t] = ar[t];
+        S.b_l[ka] = *(const T*)H.b_l.data();
+        S.b_r[ka] = *(const T*)H.b_r.data();
+        if (ka == 2) {
+            for (int t = 0; t < H.d.K_l; ++t) S.azl_pad[t] = al[t];
+            for (int t = 0; t < H.d.K_r; ++t) S.azr_pad[NQ - H.d.K_r + t] = ar[t];
+        }
+    }
+    return true;
+}
+
+template <typename T>
+bool fill_params_R(const deo_plan* plan, const int kaxis[3], bool mid, StarConfig& C) {
+    switch (C.R) {
+        case 1: return fill_params<T, 1>(plan, kaxis, mid, C);
+        case 2: return fill_params<T, 2>(plan, kaxis, mid, C);
+        case 3: return fill_params<T, 3>(plan, kaxis, mid, C);
+        case 4: return fill_params<T, 4>(plan, kaxis, mid, C);
+    }
+    return false;
+}
+
+}  // namespace
+
+// Decides whether the plan can run on the tiled kernel; if so attaches a StarConfig to it.
+int32_t star_configure(deo_plan* plan) {
+    const int nd = plan->ndims;
+    if (nd < 2 || nd > 3) return DEO_OK;
+    if (plan->accumulate) return DEO_OK;
+    const size_t es = plan->elem();
+    for (int a = 0; a < nd; ++a) if (plan->padded[a]) return DEO_OK;
+    if (((size_t)plan->dims[0] * es) % 16 != 0) return DEO_OK;          // TMA: row pitch must be a multiple of 16 bytes
+    if (plan->ops.size() > 3) return DEO_OK;
+    int R = 0, prev_axis = -1;
+    for (const HostOp& h : plan->ops) {
+        if (h.d.kind != DEO_OP_CENTERED || h.d.nonuniform) return DEO_OK;
+        if (h.d.axis <= prev_axis) return DEO_OK;                        // one operator per axis, in axis order (sum association)
+        prev_axis = h.d.axis;
+        R = R > h.d.stencil_length / 2 ? R : h.d.stencil_length / 2;
+    }
+    if (R < 1 || R > 4) return DEO_OK;
+    if (plan->slab_axis >= 0 && plan->slab_count < 3 * R + 3) return DEO_OK;
+    const bool mid = nd == 3;
+    int kaxis[3] = {0, mid ? 1 : 2, mid ? 2 : -1};                       // plan axis -> kernel axis (x, mid, march)
+    auto cfg = std::make_shared<StarConfig>();
+    cfg->R = R;
+    cfg->mid = mid;
+    cfg->sm_count = rt().sm_count;
+    const bool ok = plan->dtype == DEO_F64 ? fill_params_R<double>(plan, kaxis, mid, *cfg) : fill_params_R<float>(plan, kaxis, mid, *cfg);
+    if (!ok) return DEO_OK;
+    cfg->zchunk_pref = 64;
+    plan->star = cfg;
+    plan->kernel = "star";
+    return DEO_OK;
+}
+
+int32_t launch_star(const deo_plan* plan, void* du, const void* u, long long z0, long long z1, cudaStream_t s) {
+    StarConfig& C = *static_cast<StarConfig*>(plan->star.get());
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return DEO_ERR_CUDA; }
+    DEO_REQUIRE((reinterpret_cast<uintptr_t>(u) & 15) == 0 && (reinterpret_cast<uintptr_t>(du) & 15) == 0,
+                "star kernel: buffers must be 16-byte aligned");
+    // tensor map over the input field: (nx, ny, nz_in) for 3-D, (nx, 1, ny_in) for 2-D
+    const size_t es = plan->elem();
+    const bool mid = C.mid;
+    const cuuint64_t nx = (cuuint64_t)plan->in_dim(0);
+    const cuuint64_t d1 = mid ? (cuuint64_t)plan->in_dim(1) : 1;
+    const cuuint64_t d2 = (cuuint64_t)plan->in_dim(plan->ndims - 1);
+    cuuint64_t dims[3] = {nx, d1, d2};
+    cuuint64_t strides[2] = {nx * es, nx * d1 * es};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const int VEC = (int)(16 / es);
+    const int HX = ((C.R + VEC - 1) / VEC) * VEC;
+    cuuint32_t box[3];
+    if (mid) { box[0] = (cuuint32_t)(32 * VEC + 2 * HX); box[1] = (cuuint32_t)(8 * 4 + 2 * C.R); box[2] = 1; }
+    else { box[0] = 256; box[1] = 1; box[2] = 1; }
+    CUresult r = enc(&C.tmap, es == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(u), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return DEO_ERR_CUDA; }
+    if (!mid) { z0 = 0; z1 = plan->local_dim(plan->ndims - 1); }   // 2-D arrays stream along their last axis
+    // The one-sided rows of the march axis take their term from the register queue at the steps whose centre is
+    // global plane R (low face) / n-1-R (high face); a launch range that contains such rows but not that step
+    // (never produced by this library's own callers) runs on the per-point kernel instead.
+    {
+        const int ax = plan->ndims - 1;
+        const long long row0 = ax == plan->slab_axis ? plan->slab_start : 0;
+        const long long n = plan->dims[ax];
+        const long long g0 = z0 + row0, g1 = z1 + row0;
+        int nlow = 0, nhigh = 0;
+        for (const HostOp& h : plan->ops) if (h.d.axis == ax) { nlow = h.d.boundary_point_count; nhigh = h.d.boundary_point_count; }
+        const bool low_ok = !(nlow > 0 && g0 < nlow) || (g0 == 0 && g1 > C.R);
+        const bool high_ok = !(nhigh > 0 && g1 > n - nhigh) || (g1 == n && g0 <= n - 1 - C.R);
+        if (!low_ok || !high_ok) return launch_generic(plan, du, u, z0, z1, s);
+    }
+    return plan->dtype == DEO_F64 ? dispatch_T<double>(C, u, du, z0, z1, s) : dispatch_T<float>(C, u, du, z0, z1, s);
+}
+
 }  // namespace deo

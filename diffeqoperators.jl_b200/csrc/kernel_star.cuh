@@ -1,0 +1,675 @@
+// Tiled streaming kernel for star-shaped composites on uniform grids: Dxx [+ Dyy] [+ Dzz] (any centered
+// derivative / approximation order up to radius 4, constant coefficient) fused with affine boundary
+// conditions, ONE pass over u:
+//
+//   * x-y tiles with halo are staged into shared memory by TMA (cp.async.bulk.tensor over one 3-D tensor
+//     map of u; out-of-bounds elements are zero-filled by the hardware) through a ring of planes guarded
+//     by full/empty mbarriers; one elected thread issues the copies two planes ahead, all NWY warps compute;
+//   * 2.5-D register streaming along the slowest axis: every thread keeps the 2R+1 planes of its own
+//     columns in a register queue, so the centre plane's own values and all march-axis taps cost no load;
+//   * every thread owns PY rows x VEC contiguous points (VEC = 16 B / sizeof(T)): all shared-memory loads
+//     and global stores are 128-bit and conflict-free, the along-y taps reuse every loaded row PY times;
+//   * affine BC ghost values (ghost = b + a . u[edge], bc_operators.jl:188-191) are computed in the kernel
+//     and patched into the register windows -- no BoundaryPaddedArray is materialised;
+//   * the one-sided boundary rows (convolve_BC_left!/right!, convolutions.jl:76-118) are predicated edge
+//     paths: along x/y from the tile, along the streaming axis from the register queue (their term is
+//     added to du when the queue holds the planes they need);
+//   * 2-D arrays run the same code with no middle axis (the tile is a long x strip, streaming along y).
+//
+// Arithmetic: acc = fma(w[t], q[t], acc) over the taps in the reference's order (idx = 1..sl), operators
+// summed in A.ops order, w = (c*w) pre-multiplied as the reference forms it (convolutions.jl:47).
+#pragma once
+#include <cuda.h>
+
+#include "generic_device.cuh"
+
+namespace deo {
+
+constexpr int kStarMaxK = 8;   // BC stencil length (a_l / a_r entries) along x / y
+
+template <typename T, int R>
+struct StarParams {
+    static constexpr int NQ = 2 * R + 1, TB = 2 * R + 2;
+    int nx, ny, nz;              // local output extents along the kernel axes (x, mid, march); ny == 1 without a mid axis
+    int has[3];                  // an operator acts along kernel axis a
+    int opidx[3];                // its index in the plan
+    int in_off_z, row0_z, nglob_z, pad0_;
+    long long isy, isz, osy, osz;
+    int nlow[3], nhigh[3];       // one-sided rows
+    int K_l[3], K_r[3];
+    T a_l[3][kStarMaxK], a_r[3][kStarMaxK];
+    T b_l[3], b_r[3];
+    T azl_pad[NQ], azr_pad[NQ];  // march-axis BC stencils: a_l left-aligned, a_r right-aligned, zero padded to NQ
+    T w[3][NQ];                  // interior stencil, zero padded to the template radius
+    T bw[3][2][R][TB];           // one-sided rows [axis][low/high][row][tap]: low rows left-aligned (tap k <-> q[k]),
+                                 // high rows right-aligned (tap k <-> q[n+2-TB+k]), zero padded
+};
+
+struct StarConfig {
+    CUtensorMap tmap;
+    std::vector<unsigned char> params;
+    int R = 0;
+    bool mid = false;
+    int tx = 0, ty = 0;
+    int threads = 0;
+    size_t smem = 0;
+    int zchunk_pref = 0;
+    int sm_count = 0;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+template <typename T> struct Vec;
+template <> struct Vec<double> { using type = double2; static constexpr int N = 2; };
+template <> struct Vec<float> { using type = float4; static constexpr int N = 4; };
+
+template <typename T, int N>
+__device__ __forceinline__ void ld_vec(const T* p, T (&out)[N]) {
+    using V = typename Vec<T>::type;
+    const V v = *reinterpret_cast<const V*>(p);
+    if constexpr (N == 2) { out[0] = v.x; out[1] = v.y; }
+    else { out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w; }
+}
+template <typename T, int N>
+__device__ __forceinline__ void st_vec(T* p, const T (&in)[N]) {
+    using V = typename Vec<T>::type;
+    V v;
+    if constexpr (N == 2) { v.x = in[0]; v.y = in[1]; }
+    else { v.x = in[0]; v.y = in[1]; v.z = in[2]; v.w = in[3]; }
+    *reinterpret_cast<V*>(p) = v;
+}
+
+// Geometry shared by host and device.
+template <typename T, int R, int PY, int NWY, bool MID>
+struct StarGeom {
+    static constexpr int VEC = Vec<T>::N;
+    static constexpr int HX = ((R + VEC - 1) / VEC) * VEC;        // x halo rounded up: every window load is one 16 B vector
+    static constexpr int TX = MID ? 32 * VEC : 32 * VEC * NWY * PY;
+    static constexpr int TY = MID ? NWY * PY : 1;
+    static constexpr int PITCH = TX + 2 * HX;
+    static constexpr int ROWS = MID ? TY + 2 * R : 1;
+    static constexpr int BOXW = 256;                              // TMA box limit per dimension (elements)
+    static constexpr int NBOX = MID ? 1 : (PITCH + BOXW - 1) / BOXW;
+    static constexpr int PLANE = MID ? PITCH * ROWS : NBOX * BOXW;   // elements written per plane
+    static constexpr int PLANE_BYTES = ((PLANE * (int)sizeof(T) + 127) / 128) * 128;
+    static constexpr int NS_WANT = R + 6;                         // ring: planes z..z+R live, 4 in flight, 1 being drained
+    static constexpr int NS_FIT = (220 * 1024) / PLANE_BYTES;
+    static constexpr int NS = NS_WANT < NS_FIT ? NS_WANT : NS_FIT;
+    static constexpr int NQ = 2 * R + 1;
+    static constexpr int THREADS = NWY * 32;
+    static constexpr size_t SMEM = (size_t)NS * PLANE_BYTES + 2 * NS * sizeof(uint64_t);
+    static_assert(NS >= R + 3, "ring too small");
+};
+
+
+// x halo of one vector: exactly R values on each side of the VEC own values, as 16 B vector loads where the
+// address is 16 B aligned and one scalar load for the odd element (Float64, odd R).
+template <typename T, int R>
+__device__ __forceinline__ void load_x_halo(const T* own, T (&xw)[Vec<T>::N + 2 * R]) {
+    constexpr int VEC = Vec<T>::N;
+    if constexpr (VEC == 2) {
+        constexpr int NV = R / 2;
+        if constexpr (R % 2 == 1) { xw[0] = own[-R]; xw[R + VEC + R - 1] = own[VEC + R - 1]; }
+#pragma unroll
+        for (int c = 0; c < NV; ++c) {
+            T t[2];
+            ld_vec<T, 2>(own - 2 * NV + 2 * c, t);
+            xw[(R % 2) + 2 * c] = t[0]; xw[(R % 2) + 2 * c + 1] = t[1];
+            ld_vec<T, 2>(own + VEC + 2 * c, t);
+            xw[R + VEC + 2 * c] = t[0]; xw[R + VEC + 2 * c + 1] = t[1];
+        }
+    } else {
+        T l[4], r[4];
+        ld_vec<T, 4>(own - 4, l);
+        ld_vec<T, 4>(own + 4, r);
+#pragma unroll
+        for (int i = 0; i < R; ++i) { xw[i] = l[4 - R + i]; xw[R + VEC + i] = r[i]; }
+    }
+}
+
+template <typename T, int R, int PY, int NWY, bool MID>
+__global__ void __launch_bounds__(NWY * 32, 1)
+k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarParams<T, R> S,
+       const T* __restrict__ u, T* __restrict__ du, int z_begin, int z_end, int zchunk) {
+    using G = StarGeom<T, R, PY, NWY, MID>;
+    constexpr int VEC = G::VEC, HX = G::HX, PITCH = G::PITCH, NS = G::NS, NQ = G::NQ, TB = 2 * R + 2;
+    constexpr int XW = VEC + 2 * R;                        // x window of one vector: coordinates gx-R .. gx+VEC-1+R
+    constexpr int PLANE_ELEMS = G::PLANE_BYTES / (int)sizeof(T);
+    constexpr unsigned FULL = 0xffffffffu;
+
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    T* const planes = reinterpret_cast<T*>(smem_raw);      // ring of NS planes
+    uint64_t* const full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * G::PLANE_BYTES);
+    uint64_t* const empty = full + NS;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tx0 = blockIdx.x * G::TX;
+    const int ty0 = MID ? blockIdx.y * G::TY : 0;
+    const int zc0 = z_begin + blockIdx.z * zchunk;
+    const int zc1 = min(zc0 + zchunk, z_end);
+    if (zc0 >= zc1) return;
+    const int p_first = zc0 - R;                           // first plane streamed (local index)
+    const int n_planes = (zc1 - 1 + R) - p_first + 1;
+
+    // TMA producer = thread 0 (inline): plane ring index kk -> slot kk % NS
+    auto issue_plane = [&](int kk) {
+        const int slot = kk % NS;
+        mbar_expect_tx(&full[slot], (uint32_t)(G::PLANE * sizeof(T)));
+        const int pz = p_first + kk + S.in_off_z;
+        T* dst = planes + (size_t)slot * PLANE_ELEMS;
+        if constexpr (MID) {
+            tma_load_3d(dst, &tmap, &full[slot], tx0 - HX, ty0 - R, pz);
+        } else {
+#pragma unroll
+            for (int b = 0; b < G::NBOX; ++b)              // the strip is wider than one TMA box: fixed-width pieces
+                tma_load_3d(dst + b * G::BOXW, &tmap, &full[slot], tx0 - HX + b * G::BOXW, 0, pz);
+        }
+    };
+    int k_issue = 0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NWY); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (; k_issue < NS && k_issue < n_planes; ++k_issue) issue_plane(k_issue);
+    }
+    __syncthreads();
+
+    const int wy = warp;
+    const int nx = S.nx, ny = S.ny;
+    // this thread's PY vectors: global x, y, and the offset of the vector inside a shared-memory plane
+    int gx[PY], gy[PY], soff[PY];
+    bool live[PY];
+    long long obase[PY];
+#pragma unroll
+    for (int j = 0; j < PY; ++j) {
+        if constexpr (MID) {
+            gx[j] = tx0 + lane * VEC;
+            gy[j] = ty0 + wy * PY + j;
+            soff[j] = (R + wy * PY + j) * PITCH + HX + lane * VEC;
+        } else {
+            const int seg = (j * NWY + wy) * 32 + lane;
+            gx[j] = tx0 + seg * VEC;
+            gy[j] = 0;
+            soff[j] = HX + seg * VEC;
+        }
+        live[j] = gx[j] < nx && gy[j] < ny;
+        obase[j] = (long long)gx[j] + (long long)gy[j] * S.osy;
+    }
+    const bool has_x = S.has[0] != 0, has_y = MID && S.has[1] != 0, has_z = S.has[2] != 0;
+    // CTA-uniform edge flags: only tiles on a face execute the edge code at all
+    const bool xlo_tile = has_x && tx0 == 0, xhi_tile = has_x && tx0 + G::TX >= nx;
+    const bool ylo_tile = has_y && ty0 == 0, yhi_tile = has_y && ty0 + G::TY >= ny;
+
+    // register queue: zq[j][v][t] = plane z-R+t of this thread's columns (t = R is the centre plane)
+    T zq[PY][VEC][NQ];
+#pragma unroll
+    for (int j = 0; j < PY; ++j)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+#pragma unroll
+            for (int t = 0; t < NQ; ++t) zq[j][v][t] = T(0);
+
+#pragma unroll 1
+    for (int z = zc0 - 2 * R; z < zc1; ++z) {              // z = centre plane of this step (local index)
+        const int ka = z + R - p_first;                    // ring index of the plane acquired in this step
+        // --- acquire plane z+R: shift the queue, append this thread's values --------------------------
+        {
+            const int slot_new = ka % NS;
+            mbar_wait(&full[slot_new], (ka / NS) & 1);
+            const T* pn = planes + (size_t)slot_new * PLANE_ELEMS;
+            const int gzn = z + R + S.row0_z;              // global index of the new plane along the march axis
+#pragma unroll
+            for (int j = 0; j < PY; ++j) {
+                T val[VEC];
+                ld_vec<T, VEC>(pn + soff[j], val);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+#pragma unroll
+                    for (int t = 0; t < NQ - 1; ++t) zq[j][v][t] = zq[j][v][t + 1];
+                    zq[j][v][NQ - 1] = val[v];
+                }
+            }
+            if (has_z && (gzn == -1 || gzn == S.nglob_z)) {   // the plane just outside a physical face is the BC ghost plane
+                const bool high = gzn != -1;
+                const int K = high ? S.K_r[2] : S.K_l[2];
+                const T* a = high ? S.a_r[2] : S.a_l[2];
+                const T b = high ? S.b_r[2] : S.b_l[2];
+                const long long p0 = (long long)((high ? S.nglob_z - K : 0) - S.row0_z + S.in_off_z) * S.isz;
+#pragma unroll
+                for (int j = 0; j < PY; ++j) {
+                    if (!live[j]) continue;
+                    const T* col = u + (long long)gx[j] + (long long)gy[j] * S.isy + p0;
+                    T acc[VEC];
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) acc[v] = T(0);
+#pragma unroll 1
+                    for (int k = 0; k < K; ++k) {
+                        T val[VEC];
+                        ld_vec<T, VEC>(col + (long long)k * S.isz, val);
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) acc[v] = fma_t(a[k], val[v], acc[v]);
+                    }
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) zq[j][v][NQ - 1] = acc[v] + b;
+                }
+            }
+            if (ka < R) {                                  // planes below the chunk only feed the queue: free the slot now
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[slot_new]);
+            }
+        }
+        if (z >= zc0) {
+            // --- centre plane z ------------------------------------------------------------------------
+            const int kc = ka - R;                         // its ring index
+            const T* pl = planes + (size_t)(kc % NS) * PLANE_ELEMS;
+            const int gz = z + S.row0_z;
+            const bool z_low_edge = has_z && gz < S.nlow[2];
+            const bool z_high_edge = has_z && gz >= S.nglob_z - S.nhigh[2];
+            T tot[PY][VEC];
+            bool first = true;
+            // ================= x operator: window = [R halo | VEC own (already in the queue) | R halo] =================
+            if (has_x) {
+                // x ghosts of this warp's rows, computed by lanes 0..PY-1 (low face) and PY..2PY-1 (high face)
+                T gsrc = T(0);
+                if constexpr (MID) {
+                    if (xlo_tile || xhi_tile) {
+                        const bool high = lane >= PY;
+                        if (lane < 2 * PY && (high ? xhi_tile : xlo_tile)) {
+                            const T* row = pl + (R + wy * PY + (lane % PY)) * PITCH + HX - tx0;   // row[x] = value at global x
+                            const int K = high ? S.K_r[0] : S.K_l[0];
+                            const T* a = high ? S.a_r[0] : S.a_l[0];
+                            const int x0 = high ? nx - K : 0;
+                            T acc = T(0);
+#pragma unroll 1
+                            for (int k = 0; k < K; ++k) acc = fma_t(a[k], row[x0 + k], acc);
+                            gsrc = acc + (high ? S.b_r[0] : S.b_l[0]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < PY; ++j) {
+                    T xw[XW];
+                    load_x_halo<T, R>(pl + soff[j], xw);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) xw[R + v] = zq[j][v][R];
+                    if constexpr (MID) {
+                        if (xlo_tile) {                    // the interior window of the first lanes reaches the low ghost
+                            const T g = __shfl_sync(FULL, gsrc, j);
+#pragma unroll
+                            for (int i = 0; i < R; ++i) if (gx[j] - R + i == -1) xw[i] = g;
+                        }
+                        if (xhi_tile) {
+                            const T g = __shfl_sync(FULL, gsrc, PY + j);
+#pragma unroll
+                            for (int i = R + VEC; i < XW; ++i) if (gx[j] - R + i == nx) xw[i] = g;
+                        }
+                    } else {
+                        if ((xlo_tile && gx[j] - R <= -1) || (xhi_tile && live[j] && gx[j] + VEC - 1 + R >= nx)) {
+                            const bool high = gx[j] - R > -1;
+                            const int K = high ? S.K_r[0] : S.K_l[0];
+                            const T* a = high ? S.a_r[0] : S.a_l[0];
+                            const T* row = pl + HX - tx0 + (high ? nx - K : 0);
+                            T acc = T(0);
+#pragma unroll 1
+                            for (int k = 0; k < K; ++k) acc = fma_t(a[k], row[k], acc);
+                            const T g = acc + (high ? S.b_r[0] : S.b_l[0]);
+#pragma unroll
+                            for (int i = 0; i < XW; ++i) if (gx[j] - R + i == (high ? nx : -1)) xw[i] = g;
+                        }
+                    }
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        T a = T(0);
+#pragma unroll
+                        for (int t = 0; t < NQ; ++t) a = fma_t(S.w[0][t], xw[v + t], a);
+                        tot[j][v] = a;
+                    }
+                }
+                // one-sided rows (convolve_BC_left!/right!): x < nlow and x >= nx - nhigh
+                if ((xlo_tile && S.nlow[0] > 0) || (xhi_tile && S.nhigh[0] > 0)) {
+                    if constexpr (MID) {
+                        // cooperative: lane e computes one whole row-sum from the tile, the owner lane picks it up by shuffle
+                        constexpr int NE = PY * R;         // items per face: (row j, one-sided row r)
+                        const int side = lane / NE, jj = (lane % NE) / R, r = lane % R;
+                        const T gsel = __shfl_sync(FULL, gsrc, (side ? PY : 0) + jj);
+                        T res = T(0);
+                        if (side < 2 && (side ? (xhi_tile && r < S.nhigh[0]) : (xlo_tile && r < S.nlow[0]))) {
+                            const T* row = pl + (R + wy * PY + jj) * PITCH + HX - tx0;
+                            const T* w = S.bw[0][side][r];
+                            if (!side) {                   // q[0] = low ghost, q[k] = u[k-1]
+                                res = fma_t(w[0], gsel, T(0));
+#pragma unroll 1
+                                for (int k = 1; k < TB; ++k) res = fma_t(w[k], row[k - 1], res);
+                            } else {                       // q[n+2-TB+k] = u[n+1-TB+k], last tap = high ghost
+#pragma unroll 1
+                                for (int k = 0; k < TB - 1; ++k) res = fma_t(w[k], row[nx + 1 - TB + k], res);
+                                res = fma_t(w[TB - 1], gsel, res);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < PY; ++j) {
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) {
+                                const int xg = gx[j] + v;
+                                const bool lo = xlo_tile && xg < S.nlow[0];
+                                const bool hi = xhi_tile && xg >= nx - S.nhigh[0] && xg < nx;
+                                const int e = lo ? j * R + xg : (hi ? NE + j * R + (xg - (nx - S.nhigh[0])) : 0);
+                                const T val = __shfl_sync(FULL, res, e);
+                                if (lo || hi) tot[j][v] = val;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < PY; ++j) {
+                            if (!live[j]) continue;
+                            if (!((xlo_tile && gx[j] < S.nlow[0]) || (xhi_tile && gx[j] + VEC - 1 >= nx - S.nhigh[0]))) continue;
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) {
+                                const int xg = gx[j] + v;
+                                const bool high = xg >= nx - S.nhigh[0];
+                                if (!(high || xg < S.nlow[0])) continue;
+                                const T* row = pl + HX - tx0;
+                                const T* w = S.bw[0][high ? 1 : 0][high ? xg - (nx - S.nhigh[0]) : xg];
+                                const int K = high ? S.K_r[0] : S.K_l[0];
+                                const T* a = high ? S.a_r[0] : S.a_l[0];
+                                T g = T(0);
+#pragma unroll 1
+                                for (int k = 0; k < K; ++k) g = fma_t(a[k], row[(high ? nx - K : 0) + k], g);
+                                g = g + (high ? S.b_r[0] : S.b_l[0]);
+                                T res = T(0);
+#pragma unroll 1
+                                for (int k = 0; k < TB; ++k) {
+                                    const int c = high ? nx + 1 - TB + k : k - 1;
+                                    res = fma_t(w[k], (c == -1 || c == nx) ? g : row[c], res);
+                                }
+                                tot[j][v] = res;
+                            }
+                        }
+                    }
+                }
+                first = false;
+            }
+            // ================= y operator: 2R halo rows loaded once, own rows from the queue =================
+            if constexpr (MID) {
+                if (has_y) {
+                    T acc[PY][VEC];
+#pragma unroll
+                    for (int j = 0; j < PY; ++j)
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) acc[j][v] = T(0);
+                    T gylo[VEC], gyhi[VEC];                // y ghosts of this thread's columns
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) { gylo[v] = T(0); gyhi[v] = T(0); }
+                    const T* colbase = pl + (R - ty0) * PITCH + HX + lane * VEC;   // colbase[y*PITCH + v] = value at global row y
+                    if (ylo_tile) {
+#pragma unroll 1
+                        for (int k = 0; k < S.K_l[1]; ++k) {
+                            T val[VEC];
+                            ld_vec<T, VEC>(colbase + k * PITCH, val);
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) gylo[v] = fma_t(S.a_l[1][k], val[v], gylo[v]);
+                        }
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) gylo[v] += S.b_l[1];
+                    }
+                    if (yhi_tile) {
+#pragma unroll 1
+                        for (int k = 0; k < S.K_r[1]; ++k) {
+                            T val[VEC];
+                            ld_vec<T, VEC>(colbase + (ny - S.K_r[1] + k) * PITCH, val);
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) gyhi[v] = fma_t(S.a_r[1][k], val[v], gyhi[v]);
+                        }
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) gyhi[v] += S.b_r[1];
+                    }
+#pragma unroll
+                    for (int r = 0; r < PY + 2 * R; ++r) {
+                        T row[VEC];
+                        if (r >= R && r < R + PY) {
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) row[v] = zq[r - R][v][R];
+                        } else {
+                            ld_vec<T, VEC>(pl + soff[0] + (r - R) * PITCH, row);
+                            const int yg = gy[0] - R + r;
+                            if (ylo_tile && yg == -1) {
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v) row[v] = gylo[v];
+                            }
+                            if (yhi_tile && yg == ny) {
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v) row[v] = gyhi[v];
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < PY; ++j) {
+                            const int t = r - j;
+                            if (t >= 0 && t < NQ) {
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v) acc[j][v] = fma_t(S.w[1][t], row[v], acc[j][v]);
+                            }
+                        }
+                    }
+                    if ((ylo_tile && S.nlow[1] > 0) || (yhi_tile && S.nhigh[1] > 0)) {
+#pragma unroll
+                        for (int j = 0; j < PY; ++j) {
+                            const bool lo = ylo_tile && gy[j] < S.nlow[1];
+                            const bool hi = yhi_tile && gy[j] >= ny - S.nhigh[1] && gy[j] < ny;
+                            if (!(lo || hi)) continue;     // warp-uniform: a row belongs to one warp
+                            const T* w = S.bw[1][hi ? 1 : 0][hi ? gy[j] - (ny - S.nhigh[1]) : gy[j]];
+                            T res[VEC];
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) res[v] = T(0);
+#pragma unroll 1
+                            for (int k = 0; k < TB; ++k) {
+                                const int c = hi ? ny + 1 - TB + k : k - 1;
+                                T val[VEC];
+                                if (c == -1) { for (int v = 0; v < VEC; ++v) val[v] = gylo[v]; }
+                                else if (c == ny) { for (int v = 0; v < VEC; ++v) val[v] = gyhi[v]; }
+                                else ld_vec<T, VEC>(colbase + c * PITCH, val);
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v) res[v] = fma_t(w[k], val[v], res[v]);
+                            }
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) acc[j][v] = res[v];
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < PY; ++j)
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) tot[j][v] = first ? acc[j][v] : tot[j][v] + acc[j][v];
+                    first = false;
+                }
+            }
+            // ================= march-axis operator from the register queue =================
+            // (its one-sided rows take their term from du, see below)
+            if (has_z && !z_low_edge) {
+#pragma unroll
+                for (int j = 0; j < PY; ++j) {
+                    T a[VEC];
+                    if (z_high_edge) {
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) a[v] = T(0);
+                        if (live[j]) ld_vec<T, VEC>(du + obase[j] + (long long)z * S.osz, a);
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) {
+                            T s = T(0);
+#pragma unroll
+                            for (int t = 0; t < NQ; ++t) s = fma_t(S.w[2][t], zq[j][v][t], s);
+                            a[v] = s;
+                        }
+                    }
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) tot[j][v] = first ? a[v] : tot[j][v] + a[v];
+                }
+                first = false;
+            }
+            if (first) {
+#pragma unroll
+                for (int j = 0; j < PY; ++j)
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) tot[j][v] = T(0);
+            }
+            // release the centre plane's slot, then store
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[kc % NS]);
+#pragma unroll
+            for (int j = 0; j < PY; ++j)
+                if (live[j]) st_vec<T, VEC>(du + obase[j] + (long long)z * S.osz, tot[j]);
+
+            // --- one-sided rows of the march axis, from the register queue ---------------------------------
+            // low rows r < nlow need q[0..TB-1] = ghost, planes 0..2R: exactly the queue when the centre is global plane R.
+            // Their x/y part is already in du (stored above at the steps gz = r); add the march-axis term now (it is the
+            // last operator, so the association matches the reference's sum).
+            if (has_z && S.nlow[2] > 0 && gz == R) {
+#pragma unroll
+                for (int j = 0; j < PY; ++j) {
+                    if (!live[j]) continue;
+                    T gl[VEC];
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        T s = T(0);
+#pragma unroll
+                        for (int m = 0; m < NQ; ++m) s = fma_t(S.azl_pad[m], zq[j][v][m], s);
+                        gl[v] = s + S.b_l[2];
+                    }
+#pragma unroll 1
+                    for (int r = 0; r < S.nlow[2]; ++r) {
+                        T* dst = du + obase[j] + (long long)(r - S.row0_z) * S.osz;
+                        T old[VEC];
+                        ld_vec<T, VEC>(dst, old);
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) {
+                            T s = fma_t(S.bw[2][0][r][0], gl[v], T(0));
+#pragma unroll
+                            for (int kk = 1; kk < TB; ++kk) s = fma_t(S.bw[2][0][r][kk], zq[j][v][kk - 1], s);
+                            old[v] = old[v] + s;
+                        }
+                        st_vec<T, VEC>(dst, old);
+                    }
+                }
+            }
+            // high rows need planes n-1-2R..n-1 and the high ghost: the queue when the centre is global plane n-1-R.
+            // Their term is parked in du now and picked up (tot + du) when those rows are computed a few steps later.
+            if (has_z && S.nhigh[2] > 0 && gz == S.nglob_z - 1 - R) {
+#pragma unroll
+                for (int j = 0; j < PY; ++j) {
+                    if (!live[j]) continue;
+                    T gh[VEC];
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        T s = T(0);
+#pragma unroll
+                        for (int m = 0; m < NQ; ++m) s = fma_t(S.azr_pad[m], zq[j][v][m], s);
+                        gh[v] = s + S.b_r[2];
+                    }
+#pragma unroll 1
+                    for (int r = 0; r < S.nhigh[2]; ++r) {
+                        T* dst = du + obase[j] + (long long)(S.nglob_z - S.nhigh[2] + r - S.row0_z) * S.osz;
+                        T out[VEC];
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) {
+                            T s = T(0);
+#pragma unroll
+                            for (int kk = 0; kk < TB - 1; ++kk) s = fma_t(S.bw[2][1][r][kk], zq[j][v][kk], s);
+                            out[v] = fma_t(S.bw[2][1][r][TB - 1], gh[v], s);
+                        }
+                        st_vec<T, VEC>(dst, out);
+                    }
+                }
+            }
+        }
+        // --- producer: refill the slot drained one step ago (all warps have normally released it by now) ----
+        if (threadIdx.x == 0) {
+            const int kc_done = ka - R;                    // ring index of the centre just released by this warp (< 0 while priming)
+            while (k_issue < n_planes && k_issue - NS <= kc_done - 1) {
+                const int slot = k_issue % NS;
+                mbar_wait(&empty[slot], ((k_issue / NS) - 1) & 1);
+                issue_plane(k_issue);
+                ++k_issue;
+            }
+        }
+    }
+}
+
+template <typename T, int R, int PY, int NWY, bool MID>
+int32_t launch_variant(const StarConfig& C, const void* u, void* du, long long z0, long long z1, cudaStream_t s) {
+    using G = StarGeom<T, R, PY, NWY, MID>;
+    const StarParams<T, R>& S = *reinterpret_cast<const StarParams<T, R>*>(C.params.data());
+    static bool attr_set = false;
+    auto kern = k_star<T, R, PY, NWY, MID>;
+    if (!attr_set) {
+        DEO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
+        attr_set = true;
+    }
+    // the tensor map addresses the buffer it was encoded for; re-encode when the caller passes another one
+    CUtensorMap map = C.tmap;
+    const long long len = z1 - z0;
+    const long long tiles = (long long)((S.nx + G::TX - 1) / G::TX) * (MID ? (S.ny + G::TY - 1) / G::TY : 1);
+    // chunking of the march axis: fill the SMs, keep the 2R priming planes per chunk cheap, never cut a face's one-sided rows
+    long long zc = C.zchunk_pref;
+    {
+        double best = 1e30;
+        long long best_zc = len;
+        for (long long nch = 1; nch <= len; ++nch) {
+            long long c = (len + nch - 1) / nch;
+            if (c < 4 * R + 4 && nch > 1) break;
+            const long long nchunks = (len + c - 1) / c;
+            const long long last = len - (nchunks - 1) * c;
+            if (nchunks > 1 && last < R + 1) continue;
+            const long long ctas = tiles * nchunks;
+            const long long waves = (ctas + C.sm_count - 1) / C.sm_count;
+            const double cost = (double)waves * (double)(c + 2 * R);   // makespan in plane-steps (each CTA also primes 2R planes)
+            if (cost < best - 1e-12) { best = cost; best_zc = c; }
+            if (ctas > 64LL * C.sm_count) break;
+        }
+        zc = best_zc;
+    }
+    dim3 grid((unsigned)((S.nx + G::TX - 1) / G::TX), (unsigned)(MID ? (S.ny + G::TY - 1) / G::TY : 1), (unsigned)((len + zc - 1) / zc));
+    kern<<<grid, G::THREADS, G::SMEM, s>>>(map, S, (const T*)u, (T*)du, (int)z0, (int)z1, (int)zc);
+    DEO_CUDA(cudaGetLastError());
+    return DEO_OK;
+}
+
+
+// One translation unit per radius instantiates these (star_inst_R*.cu), so the variants compile in parallel.
+template <typename T, int R>
+int32_t star_launch_R(const StarConfig& C, const void* u, void* du, long long z0, long long z1, cudaStream_t s);
+
+#define DEO_STAR_INSTANTIATE(R_)                                                                                              \
+    template <typename T, int R>                                                                                              \
+    int32_t star_launch_R(const StarConfig& C, const void* u, void* du, long long z0, long long z1, cudaStream_t s) {        \
+        if (C.mid) return launch_variant<T, R, 4, 8, true>(C, u, du, z0, z1, s);                                              \
+        return launch_variant<T, R, 4, 8, false>(C, u, du, z0, z1, s);                                                        \
+    }                                                                                                                          \
+    template int32_t star_launch_R<double, R_>(const StarConfig&, const void*, void*, long long, long long, cudaStream_t);    \
+    template int32_t star_launch_R<float, R_>(const StarConfig&, const void*, void*, long long, long long, cudaStream_t);
+
+}  // namespace deo

@@ -1,0 +1,6 @@
+// Instantiates the tiled kernel for stencil radius 2 (Float32 and Float64, 3-D tile and 2-D strip).
+#include "kernel_star.cuh"
+
+namespace deo {
+DEO_STAR_INSTANTIATE(2)
+}  // namespace deo
