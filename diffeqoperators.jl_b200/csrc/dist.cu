@@ -154,6 +154,14 @@ int32_t dist_apply(deo_plan* plan, deo_buffer* du, deo_buffer* u) {
     const long long cnt = plan->slab_count;
     const int H = plan->halo;
     deo_dist* ctx = plan->dist;
+    // The halo planes outside a physical face are never part of a result, but the tiled kernel streams them
+    // through its pipeline (multiplied by zero weights at most): keep them finite.
+    if (H > 0) {
+        const size_t plane_b = (size_t)plan->in_dim(0) * (size_t)plan->in_dim(1) * plan->elem();
+        if (plan->rank == 0) DEO_CUDA(cudaMemsetAsync(u->ptr, 0, (size_t)H * plane_b, R.stream));
+        if (plan->rank == plan->nranks - 1)
+            DEO_CUDA(cudaMemsetAsync((char*)u->ptr + (size_t)(cnt + H) * plane_b, 0, (size_t)H * plane_b, R.stream));
+    }
     if (!ctx || plan->nranks == 1 || H == 0) {   // local emulation or single rank: halos are the caller's business
         g_launches += 1;
         return launch_plan(plan, du->ptr, u->ptr, 0, cnt, R.stream);

@@ -1,4 +1,6 @@
 // Host side of the tiled streaming kernel (kernel_star.cuh): eligibility, parameter packing, tensor map, dispatch.
+#include <cstdlib>
+
 #include "kernel_star.cuh"
 
 namespace deo {
@@ -53,33 +55,44 @@ bool fill_params(const deo_plan* plan, const int kaxis_of_plan_axis[3], bool mid
     S.osy = mid ? P.out_stride[1] : 0;
     S.isz = P.in_stride[march_plan_axis];
     S.osz = P.out_stride[march_plan_axis];
-    for (int a = 0; a < 3; ++a) { S.has[a] = 0; S.opidx[a] = -1; S.nlow[a] = S.nhigh[a] = 0; S.K_l[a] = S.K_r[a] = 0; }
+    for (int a = 0; a < 3; ++a) { S.has[a] = 0; S.opidx[a] = -1; S.nedge[a] = 0; S.K_l[a] = S.K_r[a] = 0; }
     // the explicit rows live in device memory: fetch them back through the host copies kept in the plan
     for (int k = 0; k < P.nops; ++k) {
         const DevOp<T>& op = P.ops[k];
         const int ka = kaxis_of_plan_axis[op.axis];
         if (ka < 0 || S.has[ka]) return false;
         S.has[ka] = 1;
+        C.mask |= 1 << ka;
         S.opidx[ka] = k;
         const int r = -op.soff[0];
         if (op.mode != MODE_CONST || op.ntaps != 2 * r + 1 || r < 1 || r > R) return false;
         for (int t = 0; t < op.ntaps; ++t) S.w[ka][R - r + t] = op.w[0][t];
-        if (op.nlow > R || op.nhigh > R) return false;
-        S.nlow[ka] = op.nlow;
-        S.nhigh[ka] = op.nhigh;
+        if (op.nlow >= r + 1 || op.nhigh >= r + 1) return false;
         const int n = op.n;
         if (n < 4 * R + 4) return false;
+        S.nedge[ka] = r;                                   // rows 0..r-1 and n-r..n-1 read a ghost
         std::vector<BRow<T>> br((size_t)op.nlow + op.nhigh);
         if (!br.empty() && cudaMemcpy(br.data(), op.brows, br.size() * sizeof(BRow<T>), cudaMemcpyDeviceToHost) != cudaSuccess) return false;
-        for (int i = 0; i < op.nlow; ++i) {
-            const BRow<T>& b = br[i];
-            if (b.start != 0 || b.ntaps > TB || b.acc64) return false;
-            for (int t = 0; t < b.ntaps; ++t) S.bw[ka][0][i][t] = b.w[t];
+        for (int i = 0; i < r; ++i) {                      // low face, global row i; tap k <-> q[k]
+            if (i < op.nlow) {
+                const BRow<T>& b = br[i];
+                if (b.start != 0 || b.ntaps > TB || b.acc64) return false;
+                for (int t = 0; t < b.ntaps; ++t) S.bw[ka][0][i][t] = b.w[t];
+            } else {                                       // interior stencil whose window q[i+1-r .. i+1+r] starts at or after q[0]
+                for (int t = 0; t < op.ntaps; ++t) S.bw[ka][0][i][i + 1 - r + t] = op.w[0][t];
+            }
         }
-        for (int i = 0; i < op.nhigh; ++i) {
-            const BRow<T>& b = br[(size_t)op.nlow + i];
-            if (b.start + b.ntaps != n + 2 || b.ntaps > TB || b.acc64) return false;
-            for (int t = 0; t < b.ntaps; ++t) S.bw[ka][1][i][TB - b.ntaps + t] = b.w[t];
+        for (int i = 0; i < r; ++i) {                      // high face, global row n-r+i; tap k <-> q[n+2-TB+k]
+            const int row = n - r + i;
+            if (row >= n - op.nhigh) {
+                const BRow<T>& b = br[(size_t)op.nlow + (row - (n - op.nhigh))];
+                if (b.start + b.ntaps != n + 2 || b.ntaps > TB || b.acc64) return false;
+                for (int t = 0; t < b.ntaps; ++t) S.bw[ka][1][i][TB - b.ntaps + t] = b.w[t];
+            } else {
+                const int k0 = (row + 1 - r) - (n + 2 - TB);
+                if (k0 < 0) return false;
+                for (int t = 0; t < op.ntaps; ++t) S.bw[ka][1][i][k0 + t] = op.w[0][t];
+            }
         }
         // boundary condition of this axis
         const HostBC& H = plan->bc[op.axis];
@@ -139,8 +152,23 @@ int32_t star_configure(deo_plan* plan) {
     cfg->R = R;
     cfg->mid = mid;
     cfg->sm_count = rt().sm_count;
+    const char* env_py = getenv("DEO_STAR_PY");
+    cfg->py = env_py ? atoi(env_py) : 2;                    // 2 rows per thread, two CTAs per SM measured fastest on B200
+    if (cfg->py != 2 && cfg->py != 4) cfg->py = 2;
+    cfg->mask = 0;
     const bool ok = plan->dtype == DEO_F64 ? fill_params_R<double>(plan, kaxis, mid, *cfg) : fill_params_R<float>(plan, kaxis, mid, *cfg);
     if (!ok) return DEO_OK;
+    {
+        // the edge paths read the boundary stencils' inputs from the tile: the last (possibly partial) tile along x and y
+        // must still contain them, otherwise the per-point kernel takes the plan
+        const int VEC = (int)(16 / es), HXh = ((R + VEC - 1) / VEC) * VEC, TB = 2 * R + 2;
+        const int TX = mid ? 32 * VEC : 32 * VEC * 8 * cfg->py, TY = 8 * cfg->py;
+        const long long nx = plan->dims[0], ny = mid ? plan->dims[1] : 1;
+        const int wlast = (int)((nx - 1) % TX) + 1, hlast = (int)((ny - 1) % TY) + 1;
+        const int Kx = plan->bc[0].d.K_r, Ky = mid ? plan->bc[1].d.K_r : 0;
+        if ((cfg->mask & 1) && (wlast + HXh < TB - 1 || wlast + HXh < Kx || nx < TB)) return DEO_OK;
+        if (mid && (cfg->mask & 2) && (hlast + R < TB - 1 || hlast + R < Ky || ny < TB)) return DEO_OK;
+    }
     cfg->zchunk_pref = 64;
     plan->star = cfg;
     plan->kernel = "star";
@@ -165,7 +193,7 @@ int32_t launch_star(const deo_plan* plan, void* du, const void* u, long long z0,
     const int VEC = (int)(16 / es);
     const int HX = ((C.R + VEC - 1) / VEC) * VEC;
     cuuint32_t box[3];
-    if (mid) { box[0] = (cuuint32_t)(32 * VEC + 2 * HX); box[1] = (cuuint32_t)(8 * 4 + 2 * C.R); box[2] = 1; }
+    if (mid) { box[0] = (cuuint32_t)(32 * VEC + 2 * HX); box[1] = (cuuint32_t)(8 * C.py + 2 * C.R); box[2] = 1; }
     else { box[0] = 256; box[1] = 1; box[2] = 1; }
     CUresult r = enc(&C.tmap, es == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(u), dims,
                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -181,7 +209,7 @@ int32_t launch_star(const deo_plan* plan, void* du, const void* u, long long z0,
         const long long n = plan->dims[ax];
         const long long g0 = z0 + row0, g1 = z1 + row0;
         int nlow = 0, nhigh = 0;
-        for (const HostOp& h : plan->ops) if (h.d.axis == ax) { nlow = h.d.boundary_point_count; nhigh = h.d.boundary_point_count; }
+        for (const HostOp& h : plan->ops) if (h.d.axis == ax) { nlow = h.d.stencil_length / 2; nhigh = nlow; }
         const bool low_ok = !(nlow > 0 && g0 < nlow) || (g0 == 0 && g1 > C.R);
         const bool high_ok = !(nhigh > 0 && g1 > n - nhigh) || (g1 == n && g0 <= n - 1 - C.R);
         if (!low_ok || !high_ok) return launch_generic(plan, du, u, z0, z1, s);

@@ -35,14 +35,15 @@ struct StarParams {
     int opidx[3];                // its index in the plan
     int in_off_z, row0_z, nglob_z, pad0_;
     long long isy, isz, osy, osz;
-    int nlow[3], nhigh[3];       // one-sided rows
+    int nedge[3], pad1_[3];      // rows per face whose stencil touches the ghost (= operator radius)
     int K_l[3], K_r[3];
     T a_l[3][kStarMaxK], a_r[3][kStarMaxK];
     T b_l[3], b_r[3];
     T azl_pad[NQ], azr_pad[NQ];  // march-axis BC stencils: a_l left-aligned, a_r right-aligned, zero padded to NQ
     T w[3][NQ];                  // interior stencil, zero padded to the template radius
-    T bw[3][2][R][TB];           // one-sided rows [axis][low/high][row][tap]: low rows left-aligned (tap k <-> q[k]),
-                                 // high rows right-aligned (tap k <-> q[n+2-TB+k]), zero padded
+    T bw[3][2][R][TB];           // ghost-touching rows [axis][low/high][row][tap] (one-sided boundary rows and the interior
+                                 // rows next to them): low rows left-aligned (tap k <-> q[k]), high rows right-aligned
+                                 // (tap k <-> q[n+2-TB+k]; row i is global row n-nedge+i), zero padded
 };
 
 struct StarConfig {
@@ -50,9 +51,8 @@ struct StarConfig {
     std::vector<unsigned char> params;
     int R = 0;
     bool mid = false;
-    int tx = 0, ty = 0;
-    int threads = 0;
-    size_t smem = 0;
+    int py = 4;              // rows (or x segments) per thread: 4 -> one CTA per SM, 2 -> two CTAs per SM
+    int mask = 0;            // bit a: an operator acts along kernel axis a (x, mid, march)
     int zchunk_pref = 0;
     int sm_count = 0;
 };
@@ -120,7 +120,7 @@ struct StarGeom {
     static constexpr int PLANE = MID ? PITCH * ROWS : NBOX * BOXW;   // elements written per plane
     static constexpr int PLANE_BYTES = ((PLANE * (int)sizeof(T) + 127) / 128) * 128;
     static constexpr int NS_WANT = R + 6;                         // ring: planes z..z+R live, 4 in flight, 1 being drained
-    static constexpr int NS_FIT = (220 * 1024) / PLANE_BYTES;
+    static constexpr int NS_FIT = ((PY <= 2 ? 110 : 220) * 1024) / PLANE_BYTES;   // PY <= 2 variants run two CTAs per SM
     static constexpr int NS = NS_WANT < NS_FIT ? NS_WANT : NS_FIT;
     static constexpr int NQ = 2 * R + 1;
     static constexpr int THREADS = NWY * 32;
@@ -154,8 +154,8 @@ __device__ __forceinline__ void load_x_halo(const T* own, T (&xw)[Vec<T>::N + 2 
     }
 }
 
-template <typename T, int R, int PY, int NWY, bool MID>
-__global__ void __launch_bounds__(NWY * 32, 1)
+template <typename T, int R, int PY, int NWY, bool MID, int MASK>
+__global__ void __launch_bounds__(NWY * 32, (PY <= 2 ? 2 : 1))
 k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarParams<T, R> S,
        const T* __restrict__ u, T* __restrict__ du, int z_begin, int z_end, int zchunk) {
     using G = StarGeom<T, R, PY, NWY, MID>;
@@ -163,6 +163,8 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
     constexpr int XW = VEC + 2 * R;                        // x window of one vector: coordinates gx-R .. gx+VEC-1+R
     constexpr int PLANE_ELEMS = G::PLANE_BYTES / (int)sizeof(T);
     constexpr unsigned FULL = 0xffffffffu;
+    // which kernel axes carry an operator is a compile-time property of the variant (MASK bit a = kernel axis a)
+    constexpr bool has_x = (MASK & 1) != 0, has_y = MID && (MASK & 2) != 0, has_z = (MASK & 4) != 0;
 
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     T* const planes = reinterpret_cast<T*>(smem_raw);      // ring of NS planes
@@ -205,7 +207,7 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
     // this thread's PY vectors: global x, y, and the offset of the vector inside a shared-memory plane
     int gx[PY], gy[PY], soff[PY];
     bool live[PY];
-    long long obase[PY];
+    T* optr[PY];                                           // output pointer of each vector at plane zc0
 #pragma unroll
     for (int j = 0; j < PY; ++j) {
         if constexpr (MID) {
@@ -219,12 +221,12 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
             soff[j] = HX + seg * VEC;
         }
         live[j] = gx[j] < nx && gy[j] < ny;
-        obase[j] = (long long)gx[j] + (long long)gy[j] * S.osy;
+        optr[j] = du + (long long)gx[j] + (long long)gy[j] * S.osy + (long long)zc0 * S.osz;
     }
-    const bool has_x = S.has[0] != 0, has_y = MID && S.has[1] != 0, has_z = S.has[2] != 0;
-    // CTA-uniform edge flags: only tiles on a face execute the edge code at all
+    // CTA-uniform face flags: only tiles on a face execute any edge code
     const bool xlo_tile = has_x && tx0 == 0, xhi_tile = has_x && tx0 + G::TX >= nx;
     const bool ylo_tile = has_y && ty0 == 0, yhi_tile = has_y && ty0 + G::TY >= ny;
+    const int ex = S.nedge[0], ey = S.nedge[1], ez = S.nedge[2];   // rows per face whose stencil touches the ghost
 
     // register queue: zq[j][v][t] = plane z-R+t of this thread's columns (t = R is the centre plane)
     T zq[PY][VEC][NQ];
@@ -235,15 +237,14 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
 #pragma unroll
             for (int t = 0; t < NQ; ++t) zq[j][v][t] = T(0);
 
+    int ka = 0;                                            // ring index of the plane acquired in this step
 #pragma unroll 1
-    for (int z = zc0 - 2 * R; z < zc1; ++z) {              // z = centre plane of this step (local index)
-        const int ka = z + R - p_first;                    // ring index of the plane acquired in this step
+    for (int z = zc0 - 2 * R; z < zc1; ++z, ++ka) {        // z = centre plane of this step (local index)
         // --- acquire plane z+R: shift the queue, append this thread's values --------------------------
         {
             const int slot_new = ka % NS;
             mbar_wait(&full[slot_new], (ka / NS) & 1);
             const T* pn = planes + (size_t)slot_new * PLANE_ELEMS;
-            const int gzn = z + R + S.row0_z;              // global index of the new plane along the march axis
 #pragma unroll
             for (int j = 0; j < PY; ++j) {
                 T val[VEC];
@@ -253,30 +254,6 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
 #pragma unroll
                     for (int t = 0; t < NQ - 1; ++t) zq[j][v][t] = zq[j][v][t + 1];
                     zq[j][v][NQ - 1] = val[v];
-                }
-            }
-            if (has_z && (gzn == -1 || gzn == S.nglob_z)) {   // the plane just outside a physical face is the BC ghost plane
-                const bool high = gzn != -1;
-                const int K = high ? S.K_r[2] : S.K_l[2];
-                const T* a = high ? S.a_r[2] : S.a_l[2];
-                const T b = high ? S.b_r[2] : S.b_l[2];
-                const long long p0 = (long long)((high ? S.nglob_z - K : 0) - S.row0_z + S.in_off_z) * S.isz;
-#pragma unroll
-                for (int j = 0; j < PY; ++j) {
-                    if (!live[j]) continue;
-                    const T* col = u + (long long)gx[j] + (long long)gy[j] * S.isy + p0;
-                    T acc[VEC];
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) acc[v] = T(0);
-#pragma unroll 1
-                    for (int k = 0; k < K; ++k) {
-                        T val[VEC];
-                        ld_vec<T, VEC>(col + (long long)k * S.isz, val);
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) acc[v] = fma_t(a[k], val[v], acc[v]);
-                    }
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) zq[j][v][NQ - 1] = acc[v] + b;
                 }
             }
             if (ka < R) {                                  // planes below the chunk only feed the queue: free the slot now
@@ -289,60 +266,15 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
             const int kc = ka - R;                         // its ring index
             const T* pl = planes + (size_t)(kc % NS) * PLANE_ELEMS;
             const int gz = z + S.row0_z;
-            const bool z_low_edge = has_z && gz < S.nlow[2];
-            const bool z_high_edge = has_z && gz >= S.nglob_z - S.nhigh[2];
             T tot[PY][VEC];
-            bool first = true;
             // ================= x operator: window = [R halo | VEC own (already in the queue) | R halo] =================
-            if (has_x) {
-                // x ghosts of this warp's rows, computed by lanes 0..PY-1 (low face) and PY..2PY-1 (high face)
-                T gsrc = T(0);
-                if constexpr (MID) {
-                    if (xlo_tile || xhi_tile) {
-                        const bool high = lane >= PY;
-                        if (lane < 2 * PY && (high ? xhi_tile : xlo_tile)) {
-                            const T* row = pl + (R + wy * PY + (lane % PY)) * PITCH + HX - tx0;   // row[x] = value at global x
-                            const int K = high ? S.K_r[0] : S.K_l[0];
-                            const T* a = high ? S.a_r[0] : S.a_l[0];
-                            const int x0 = high ? nx - K : 0;
-                            T acc = T(0);
-#pragma unroll 1
-                            for (int k = 0; k < K; ++k) acc = fma_t(a[k], row[x0 + k], acc);
-                            gsrc = acc + (high ? S.b_r[0] : S.b_l[0]);
-                        }
-                    }
-                }
+            if constexpr (has_x) {
 #pragma unroll
                 for (int j = 0; j < PY; ++j) {
                     T xw[XW];
                     load_x_halo<T, R>(pl + soff[j], xw);
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) xw[R + v] = zq[j][v][R];
-                    if constexpr (MID) {
-                        if (xlo_tile) {                    // the interior window of the first lanes reaches the low ghost
-                            const T g = __shfl_sync(FULL, gsrc, j);
-#pragma unroll
-                            for (int i = 0; i < R; ++i) if (gx[j] - R + i == -1) xw[i] = g;
-                        }
-                        if (xhi_tile) {
-                            const T g = __shfl_sync(FULL, gsrc, PY + j);
-#pragma unroll
-                            for (int i = R + VEC; i < XW; ++i) if (gx[j] - R + i == nx) xw[i] = g;
-                        }
-                    } else {
-                        if ((xlo_tile && gx[j] - R <= -1) || (xhi_tile && live[j] && gx[j] + VEC - 1 + R >= nx)) {
-                            const bool high = gx[j] - R > -1;
-                            const int K = high ? S.K_r[0] : S.K_l[0];
-                            const T* a = high ? S.a_r[0] : S.a_l[0];
-                            const T* row = pl + HX - tx0 + (high ? nx - K : 0);
-                            T acc = T(0);
-#pragma unroll 1
-                            for (int k = 0; k < K; ++k) acc = fma_t(a[k], row[k], acc);
-                            const T g = acc + (high ? S.b_r[0] : S.b_l[0]);
-#pragma unroll
-                            for (int i = 0; i < XW; ++i) if (gx[j] - R + i == (high ? nx : -1)) xw[i] = g;
-                        }
-                    }
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) {
                         T a = T(0);
@@ -351,25 +283,31 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
                         tot[j][v] = a;
                     }
                 }
-                // one-sided rows (convolve_BC_left!/right!): x < nlow and x >= nx - nhigh
-                if ((xlo_tile && S.nlow[0] > 0) || (xhi_tile && S.nhigh[0] > 0)) {
+                // rows whose stencil touches the x ghost (x < ex, x >= nx - ex): full row sums from the tile, in q order
+                if (xlo_tile || xhi_tile) {
                     if constexpr (MID) {
-                        // cooperative: lane e computes one whole row-sum from the tile, the owner lane picks it up by shuffle
-                        constexpr int NE = PY * R;         // items per face: (row j, one-sided row r)
+                        // cooperative: lane e computes one whole row sum, the owner lane picks it up by shuffle
+                        constexpr int NE = PY * R;         // items per face: (tile row jj, edge row r)
                         const int side = lane / NE, jj = (lane % NE) / R, r = lane % R;
-                        const T gsel = __shfl_sync(FULL, gsrc, (side ? PY : 0) + jj);
                         T res = T(0);
-                        if (side < 2 && (side ? (xhi_tile && r < S.nhigh[0]) : (xlo_tile && r < S.nlow[0]))) {
-                            const T* row = pl + (R + wy * PY + jj) * PITCH + HX - tx0;
+                        if (side < 2 && r < ex && (side ? xhi_tile : xlo_tile)) {
+                            const T* row = pl + (R + wy * PY + jj) * PITCH + HX - tx0;     // row[x] = value at global x
                             const T* w = S.bw[0][side][r];
+                            const int K = side ? S.K_r[0] : S.K_l[0];
+                            const T* a = side ? S.a_r[0] : S.a_l[0];
+                            const T* arow = row + (side ? nx - K : 0);
+                            T g = T(0);
+#pragma unroll 1
+                            for (int k = 0; k < K; ++k) g = fma_t(a[k], arow[k], g);
+                            g += side ? S.b_r[0] : S.b_l[0];
                             if (!side) {                   // q[0] = low ghost, q[k] = u[k-1]
-                                res = fma_t(w[0], gsel, T(0));
+                                res = fma_t(w[0], g, T(0));
 #pragma unroll 1
                                 for (int k = 1; k < TB; ++k) res = fma_t(w[k], row[k - 1], res);
                             } else {                       // q[n+2-TB+k] = u[n+1-TB+k], last tap = high ghost
 #pragma unroll 1
                                 for (int k = 0; k < TB - 1; ++k) res = fma_t(w[k], row[nx + 1 - TB + k], res);
-                                res = fma_t(w[TB - 1], gsel, res);
+                                res = fma_t(w[TB - 1], g, res);
                             }
                         }
 #pragma unroll
@@ -377,9 +315,9 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
 #pragma unroll
                             for (int v = 0; v < VEC; ++v) {
                                 const int xg = gx[j] + v;
-                                const bool lo = xlo_tile && xg < S.nlow[0];
-                                const bool hi = xhi_tile && xg >= nx - S.nhigh[0] && xg < nx;
-                                const int e = lo ? j * R + xg : (hi ? NE + j * R + (xg - (nx - S.nhigh[0])) : 0);
+                                const bool lo = xlo_tile && xg < ex;
+                                const bool hi = xhi_tile && xg >= nx - ex && xg < nx;
+                                const int e = lo ? j * R + xg : (hi ? NE + j * R + (xg - (nx - ex)) : 0);
                                 const T val = __shfl_sync(FULL, res, e);
                                 if (lo || hi) tot[j][v] = val;
                             }
@@ -387,21 +325,20 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
                     } else {
 #pragma unroll
                         for (int j = 0; j < PY; ++j) {
-                            if (!live[j]) continue;
-                            if (!((xlo_tile && gx[j] < S.nlow[0]) || (xhi_tile && gx[j] + VEC - 1 >= nx - S.nhigh[0]))) continue;
+                            if (!live[j] || !((xlo_tile && gx[j] < ex) || (xhi_tile && gx[j] + VEC - 1 >= nx - ex))) continue;
 #pragma unroll
                             for (int v = 0; v < VEC; ++v) {
                                 const int xg = gx[j] + v;
-                                const bool high = xg >= nx - S.nhigh[0];
-                                if (!(high || xg < S.nlow[0])) continue;
+                                const bool high = xg >= nx - ex;
+                                if (!(high || xg < ex)) continue;
                                 const T* row = pl + HX - tx0;
-                                const T* w = S.bw[0][high ? 1 : 0][high ? xg - (nx - S.nhigh[0]) : xg];
+                                const T* w = S.bw[0][high ? 1 : 0][high ? xg - (nx - ex) : xg];
                                 const int K = high ? S.K_r[0] : S.K_l[0];
                                 const T* a = high ? S.a_r[0] : S.a_l[0];
                                 T g = T(0);
 #pragma unroll 1
                                 for (int k = 0; k < K; ++k) g = fma_t(a[k], row[(high ? nx - K : 0) + k], g);
-                                g = g + (high ? S.b_r[0] : S.b_l[0]);
+                                g += high ? S.b_r[0] : S.b_l[0];
                                 T res = T(0);
 #pragma unroll 1
                                 for (int k = 0; k < TB; ++k) {
@@ -413,195 +350,176 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
                         }
                     }
                 }
-                first = false;
             }
             // ================= y operator: 2R halo rows loaded once, own rows from the queue =================
-            if constexpr (MID) {
-                if (has_y) {
-                    T acc[PY][VEC];
+            if constexpr (has_y) {
+                T acc[PY][VEC];
 #pragma unroll
-                    for (int j = 0; j < PY; ++j)
+                for (int j = 0; j < PY; ++j)
 #pragma unroll
-                        for (int v = 0; v < VEC; ++v) acc[j][v] = T(0);
-                    T gylo[VEC], gyhi[VEC];                // y ghosts of this thread's columns
+                    for (int v = 0; v < VEC; ++v) acc[j][v] = T(0);
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) { gylo[v] = T(0); gyhi[v] = T(0); }
-                    const T* colbase = pl + (R - ty0) * PITCH + HX + lane * VEC;   // colbase[y*PITCH + v] = value at global row y
-                    if (ylo_tile) {
-#pragma unroll 1
-                        for (int k = 0; k < S.K_l[1]; ++k) {
-                            T val[VEC];
-                            ld_vec<T, VEC>(colbase + k * PITCH, val);
+                for (int r = 0; r < PY + 2 * R; ++r) {
+                    T row[VEC];
+                    if (r >= R && r < R + PY) {
 #pragma unroll
-                            for (int v = 0; v < VEC; ++v) gylo[v] = fma_t(S.a_l[1][k], val[v], gylo[v]);
-                        }
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) gylo[v] += S.b_l[1];
-                    }
-                    if (yhi_tile) {
-#pragma unroll 1
-                        for (int k = 0; k < S.K_r[1]; ++k) {
-                            T val[VEC];
-                            ld_vec<T, VEC>(colbase + (ny - S.K_r[1] + k) * PITCH, val);
-#pragma unroll
-                            for (int v = 0; v < VEC; ++v) gyhi[v] = fma_t(S.a_r[1][k], val[v], gyhi[v]);
-                        }
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) gyhi[v] += S.b_r[1];
+                        for (int v = 0; v < VEC; ++v) row[v] = zq[r - R][v][R];
+                    } else {
+                        ld_vec<T, VEC>(pl + soff[0] + (r - R) * PITCH, row);
                     }
 #pragma unroll
-                    for (int r = 0; r < PY + 2 * R; ++r) {
-                        T row[VEC];
-                        if (r >= R && r < R + PY) {
+                    for (int j = 0; j < PY; ++j) {
+                        const int t = r - j;
+                        if (t >= 0 && t < NQ) {
 #pragma unroll
-                            for (int v = 0; v < VEC; ++v) row[v] = zq[r - R][v][R];
-                        } else {
-                            ld_vec<T, VEC>(pl + soff[0] + (r - R) * PITCH, row);
-                            const int yg = gy[0] - R + r;
-                            if (ylo_tile && yg == -1) {
-#pragma unroll
-                                for (int v = 0; v < VEC; ++v) row[v] = gylo[v];
-                            }
-                            if (yhi_tile && yg == ny) {
-#pragma unroll
-                                for (int v = 0; v < VEC; ++v) row[v] = gyhi[v];
-                            }
-                        }
-#pragma unroll
-                        for (int j = 0; j < PY; ++j) {
-                            const int t = r - j;
-                            if (t >= 0 && t < NQ) {
-#pragma unroll
-                                for (int v = 0; v < VEC; ++v) acc[j][v] = fma_t(S.w[1][t], row[v], acc[j][v]);
-                            }
+                            for (int v = 0; v < VEC; ++v) acc[j][v] = fma_t(S.w[1][t], row[v], acc[j][v]);
                         }
                     }
-                    if ((ylo_tile && S.nlow[1] > 0) || (yhi_tile && S.nhigh[1] > 0)) {
-#pragma unroll
-                        for (int j = 0; j < PY; ++j) {
-                            const bool lo = ylo_tile && gy[j] < S.nlow[1];
-                            const bool hi = yhi_tile && gy[j] >= ny - S.nhigh[1] && gy[j] < ny;
-                            if (!(lo || hi)) continue;     // warp-uniform: a row belongs to one warp
-                            const T* w = S.bw[1][hi ? 1 : 0][hi ? gy[j] - (ny - S.nhigh[1]) : gy[j]];
-                            T res[VEC];
-#pragma unroll
-                            for (int v = 0; v < VEC; ++v) res[v] = T(0);
-#pragma unroll 1
-                            for (int k = 0; k < TB; ++k) {
-                                const int c = hi ? ny + 1 - TB + k : k - 1;
-                                T val[VEC];
-                                if (c == -1) { for (int v = 0; v < VEC; ++v) val[v] = gylo[v]; }
-                                else if (c == ny) { for (int v = 0; v < VEC; ++v) val[v] = gyhi[v]; }
-                                else ld_vec<T, VEC>(colbase + c * PITCH, val);
-#pragma unroll
-                                for (int v = 0; v < VEC; ++v) res[v] = fma_t(w[k], val[v], res[v]);
-                            }
-#pragma unroll
-                            for (int v = 0; v < VEC; ++v) acc[j][v] = res[v];
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < PY; ++j)
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) tot[j][v] = first ? acc[j][v] : tot[j][v] + acc[j][v];
-                    first = false;
                 }
+                // rows whose stencil touches the y ghost: warp-uniform (a tile row belongs to one warp)
+                if (ylo_tile || yhi_tile) {
+                    const T* colbase = pl + (R - ty0) * PITCH + HX + lane * VEC;   // colbase[y*PITCH + v] = value at global row y
+#pragma unroll
+                    for (int j = 0; j < PY; ++j) {
+                        const bool lo = ylo_tile && gy[j] < ey;
+                        const bool hi = yhi_tile && gy[j] >= ny - ey && gy[j] < ny;
+                        if (!(lo || hi)) continue;
+                        const T* w = S.bw[1][hi ? 1 : 0][hi ? gy[j] - (ny - ey) : gy[j]];
+                        const int K = hi ? S.K_r[1] : S.K_l[1];
+                        const T* a = hi ? S.a_r[1] : S.a_l[1];
+                        T g[VEC], res[VEC];
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) { g[v] = T(0); res[v] = T(0); }
+#pragma unroll 1
+                        for (int k = 0; k < K; ++k) {
+                            T val[VEC];
+                            ld_vec<T, VEC>(colbase + ((hi ? ny - K : 0) + k) * PITCH, val);
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) g[v] = fma_t(a[k], val[v], g[v]);
+                        }
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) g[v] += hi ? S.b_r[1] : S.b_l[1];
+#pragma unroll 1
+                        for (int k = 0; k < TB; ++k) {
+                            const int c = hi ? ny + 1 - TB + k : k - 1;
+                            T val[VEC];
+                            if (c == -1 || c == ny) {
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v) val[v] = g[v];
+                            } else {
+                                ld_vec<T, VEC>(colbase + c * PITCH, val);
+                            }
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) res[v] = fma_t(w[k], val[v], res[v]);
+                        }
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) acc[j][v] = res[v];
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < PY; ++j)
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) tot[j][v] = has_x ? tot[j][v] + acc[j][v] : acc[j][v];
             }
             // ================= march-axis operator from the register queue =================
-            // (its one-sided rows take their term from du, see below)
-            if (has_z && !z_low_edge) {
+            // rows whose stencil touches a march-axis ghost take their term from du (see below)
+            if constexpr (has_z) {
+                const bool z_low_edge = gz < ez, z_high_edge = gz >= S.nglob_z - ez;
+                if (!(z_low_edge || z_high_edge)) {
 #pragma unroll
-                for (int j = 0; j < PY; ++j) {
-                    T a[VEC];
-                    if (z_high_edge) {
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) a[v] = T(0);
-                        if (live[j]) ld_vec<T, VEC>(du + obase[j] + (long long)z * S.osz, a);
-                    } else {
+                    for (int j = 0; j < PY; ++j) {
 #pragma unroll
                         for (int v = 0; v < VEC; ++v) {
                             T s = T(0);
 #pragma unroll
                             for (int t = 0; t < NQ; ++t) s = fma_t(S.w[2][t], zq[j][v][t], s);
-                            a[v] = s;
+                            tot[j][v] = (has_x || has_y) ? tot[j][v] + s : s;
                         }
                     }
+                } else if (z_high_edge) {                  // the term was parked in du when the queue held its planes
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) tot[j][v] = first ? a[v] : tot[j][v] + a[v];
+                    for (int j = 0; j < PY; ++j) {
+                        T a[VEC];
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) a[v] = T(0);
+                        if (live[j]) ld_vec<T, VEC>(optr[j] + (long long)(z - zc0) * S.osz, a);
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) tot[j][v] = (has_x || has_y) ? tot[j][v] + a[v] : a[v];
+                    }
+                } else if (!(has_x || has_y)) {            // low edge row of a march-axis-only plan: its term arrives later
+#pragma unroll
+                    for (int j = 0; j < PY; ++j)
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) tot[j][v] = T(0);
                 }
-                first = false;
-            }
-            if (first) {
-#pragma unroll
-                for (int j = 0; j < PY; ++j)
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) tot[j][v] = T(0);
             }
             // release the centre plane's slot, then store
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[kc % NS]);
 #pragma unroll
             for (int j = 0; j < PY; ++j)
-                if (live[j]) st_vec<T, VEC>(du + obase[j] + (long long)z * S.osz, tot[j]);
+                if (live[j]) st_vec<T, VEC>(optr[j] + (long long)(z - zc0) * S.osz, tot[j]);
 
-            // --- one-sided rows of the march axis, from the register queue ---------------------------------
-            // low rows r < nlow need q[0..TB-1] = ghost, planes 0..2R: exactly the queue when the centre is global plane R.
-            // Their x/y part is already in du (stored above at the steps gz = r); add the march-axis term now (it is the
-            // last operator, so the association matches the reference's sum).
-            if (has_z && S.nlow[2] > 0 && gz == R) {
+            if constexpr (has_z) {
+                // --- march-axis rows that touch a ghost, from the register queue -------------------------------
+                // low rows r < ez need q[0..TB-1] = ghost, planes 0..2R: exactly the queue when the centre is global plane R.
+                // Their x/y part is already in du (stored above at the steps gz = r); add the march-axis term now (it is
+                // the last operator, so the association matches the reference's sum).
+                if (gz == R && ez > 0) {
 #pragma unroll
-                for (int j = 0; j < PY; ++j) {
-                    if (!live[j]) continue;
-                    T gl[VEC];
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) {
-                        T s = T(0);
-#pragma unroll
-                        for (int m = 0; m < NQ; ++m) s = fma_t(S.azl_pad[m], zq[j][v][m], s);
-                        gl[v] = s + S.b_l[2];
-                    }
-#pragma unroll 1
-                    for (int r = 0; r < S.nlow[2]; ++r) {
-                        T* dst = du + obase[j] + (long long)(r - S.row0_z) * S.osz;
-                        T old[VEC];
-                        ld_vec<T, VEC>(dst, old);
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) {
-                            T s = fma_t(S.bw[2][0][r][0], gl[v], T(0));
-#pragma unroll
-                            for (int kk = 1; kk < TB; ++kk) s = fma_t(S.bw[2][0][r][kk], zq[j][v][kk - 1], s);
-                            old[v] = old[v] + s;
-                        }
-                        st_vec<T, VEC>(dst, old);
-                    }
-                }
-            }
-            // high rows need planes n-1-2R..n-1 and the high ghost: the queue when the centre is global plane n-1-R.
-            // Their term is parked in du now and picked up (tot + du) when those rows are computed a few steps later.
-            if (has_z && S.nhigh[2] > 0 && gz == S.nglob_z - 1 - R) {
-#pragma unroll
-                for (int j = 0; j < PY; ++j) {
-                    if (!live[j]) continue;
-                    T gh[VEC];
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) {
-                        T s = T(0);
-#pragma unroll
-                        for (int m = 0; m < NQ; ++m) s = fma_t(S.azr_pad[m], zq[j][v][m], s);
-                        gh[v] = s + S.b_r[2];
-                    }
-#pragma unroll 1
-                    for (int r = 0; r < S.nhigh[2]; ++r) {
-                        T* dst = du + obase[j] + (long long)(S.nglob_z - S.nhigh[2] + r - S.row0_z) * S.osz;
-                        T out[VEC];
+                    for (int j = 0; j < PY; ++j) {
+                        if (!live[j]) continue;
+                        T gl[VEC];
 #pragma unroll
                         for (int v = 0; v < VEC; ++v) {
                             T s = T(0);
 #pragma unroll
-                            for (int kk = 0; kk < TB - 1; ++kk) s = fma_t(S.bw[2][1][r][kk], zq[j][v][kk], s);
-                            out[v] = fma_t(S.bw[2][1][r][TB - 1], gh[v], s);
+                            for (int m = 0; m < NQ; ++m) s = fma_t(S.azl_pad[m], zq[j][v][m], s);
+                            gl[v] = s + S.b_l[2];
                         }
-                        st_vec<T, VEC>(dst, out);
+#pragma unroll 1
+                        for (int r = 0; r < ez; ++r) {
+                            T* dst = optr[j] + (long long)(r - S.row0_z - zc0) * S.osz;
+                            T old[VEC];
+                            ld_vec<T, VEC>(dst, old);
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) {
+                                T s = fma_t(S.bw[2][0][r][0], gl[v], T(0));
+#pragma unroll
+                                for (int kk = 1; kk < TB; ++kk) s = fma_t(S.bw[2][0][r][kk], zq[j][v][kk - 1], s);
+                                old[v] = old[v] + s;
+                            }
+                            st_vec<T, VEC>(dst, old);
+                        }
+                    }
+                }
+                // high rows need planes n-1-2R..n-1 and the high ghost: the queue when the centre is global plane n-1-R.
+                // Their term is parked in du now and picked up (tot + du) when those rows are computed a few steps later.
+                if (gz == S.nglob_z - 1 - R && ez > 0) {
+#pragma unroll
+                    for (int j = 0; j < PY; ++j) {
+                        if (!live[j]) continue;
+                        T gh[VEC];
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) {
+                            T s = T(0);
+#pragma unroll
+                            for (int m = 0; m < NQ; ++m) s = fma_t(S.azr_pad[m], zq[j][v][m], s);
+                            gh[v] = s + S.b_r[2];
+                        }
+#pragma unroll 1
+                        for (int r = 0; r < ez; ++r) {
+                            T* dst = optr[j] + (long long)(S.nglob_z - ez + r - S.row0_z - zc0) * S.osz;
+                            T out[VEC];
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) {
+                                T s = T(0);
+#pragma unroll
+                                for (int kk = 0; kk < TB - 1; ++kk) s = fma_t(S.bw[2][1][r][kk], zq[j][v][kk], s);
+                                out[v] = fma_t(S.bw[2][1][r][TB - 1], gh[v], s);
+                            }
+                            st_vec<T, VEC>(dst, out);
+                        }
                     }
                 }
             }
@@ -619,12 +537,12 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
     }
 }
 
-template <typename T, int R, int PY, int NWY, bool MID>
+template <typename T, int R, int PY, int NWY, bool MID, int MASK>
 int32_t launch_variant(const StarConfig& C, const void* u, void* du, long long z0, long long z1, cudaStream_t s) {
     using G = StarGeom<T, R, PY, NWY, MID>;
     const StarParams<T, R>& S = *reinterpret_cast<const StarParams<T, R>*>(C.params.data());
     static bool attr_set = false;
-    auto kern = k_star<T, R, PY, NWY, MID>;
+    auto kern = k_star<T, R, PY, NWY, MID, MASK>;
     if (!attr_set) {
         DEO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
         attr_set = true;
@@ -645,7 +563,8 @@ int32_t launch_variant(const StarConfig& C, const void* u, void* du, long long z
             const long long last = len - (nchunks - 1) * c;
             if (nchunks > 1 && last < R + 1) continue;
             const long long ctas = tiles * nchunks;
-            const long long waves = (ctas + C.sm_count - 1) / C.sm_count;
+            const long long slots = (long long)C.sm_count * (PY <= 2 ? 2 : 1);
+            const long long waves = (ctas + slots - 1) / slots;
             const double cost = (double)waves * (double)(c + 2 * R);   // makespan in plane-steps (each CTA also primes 2R planes)
             if (cost < best - 1e-12) { best = cost; best_zc = c; }
             if (ctas > 64LL * C.sm_count) break;
@@ -663,11 +582,32 @@ int32_t launch_variant(const StarConfig& C, const void* u, void* du, long long z
 template <typename T, int R>
 int32_t star_launch_R(const StarConfig& C, const void* u, void* du, long long z0, long long z1, cudaStream_t s);
 
+template <typename T, int R, int PY, bool MID>
+int32_t star_launch_mask(const StarConfig& C, const void* u, void* du, long long z0, long long z1, cudaStream_t s) {
+    switch (C.mask) {
+        case 1: return launch_variant<T, R, PY, 8, MID, 1>(C, u, du, z0, z1, s);
+        case 4: return launch_variant<T, R, PY, 8, MID, 4>(C, u, du, z0, z1, s);
+        case 5: return launch_variant<T, R, PY, 8, MID, 5>(C, u, du, z0, z1, s);
+    }
+    if constexpr (MID) {
+        switch (C.mask) {
+            case 2: return launch_variant<T, R, PY, 8, MID, 2>(C, u, du, z0, z1, s);
+            case 3: return launch_variant<T, R, PY, 8, MID, 3>(C, u, du, z0, z1, s);
+            case 6: return launch_variant<T, R, PY, 8, MID, 6>(C, u, du, z0, z1, s);
+            case 7: return launch_variant<T, R, PY, 8, MID, 7>(C, u, du, z0, z1, s);
+        }
+    }
+    set_error("star kernel: unsupported operator mask %d", C.mask);
+    return DEO_ERR_UNSUPPORTED;
+}
+
 #define DEO_STAR_INSTANTIATE(R_)                                                                                              \
     template <typename T, int R>                                                                                              \
     int32_t star_launch_R(const StarConfig& C, const void* u, void* du, long long z0, long long z1, cudaStream_t s) {        \
-        if (C.mid) return launch_variant<T, R, 4, 8, true>(C, u, du, z0, z1, s);                                              \
-        return launch_variant<T, R, 4, 8, false>(C, u, du, z0, z1, s);                                                        \
+        if (C.py == 2) return C.mid ? star_launch_mask<T, R, 2, true>(C, u, du, z0, z1, s)                                    \
+                                    : star_launch_mask<T, R, 2, false>(C, u, du, z0, z1, s);                                  \
+        return C.mid ? star_launch_mask<T, R, 4, true>(C, u, du, z0, z1, s)                                                   \
+                     : star_launch_mask<T, R, 4, false>(C, u, du, z0, z1, s);                                                 \
     }                                                                                                                          \
     template int32_t star_launch_R<double, R_>(const StarConfig&, const void*, void*, long long, long long, cudaStream_t);    \
     template int32_t star_launch_R<float, R_>(const StarConfig&, const void*, void*, long long, long long, cudaStream_t);
