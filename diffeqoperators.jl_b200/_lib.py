@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdeo_b200.so")
+LIB_PATH = os.environ.get("DEO_LIB_PATH") or os.path.join(_HERE, "libdeo_b200.so")   # override: A/B builds
 
 DEO_OK, DEO_ERR_INVALID, DEO_ERR_CUDA, DEO_ERR_UNSUPPORTED, DEO_ERR_NCCL, DEO_ERR_NOMEM = range(6)
 DEO_F32, DEO_F64 = 0, 1

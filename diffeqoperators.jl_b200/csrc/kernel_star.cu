@@ -155,6 +155,8 @@ int32_t star_configure(deo_plan* plan) {
     const char* env_py = getenv("DEO_STAR_PY");
     cfg->py = env_py ? atoi(env_py) : 2;                    // 2 rows per thread, two CTAs per SM measured fastest on B200
     if (cfg->py != 2 && cfg->py != 4) cfg->py = 2;
+    const char* env_nwy = getenv("DEO_STAR_NWY");
+    cfg->nwy = (env_nwy && atoi(env_nwy) == 16 && cfg->py == 2) ? 16 : 8;
     cfg->mask = 0;
     const bool ok = plan->dtype == DEO_F64 ? fill_params_R<double>(plan, kaxis, mid, *cfg) : fill_params_R<float>(plan, kaxis, mid, *cfg);
     if (!ok) return DEO_OK;
@@ -162,7 +164,7 @@ int32_t star_configure(deo_plan* plan) {
         // the edge paths read the boundary stencils' inputs from the tile: the last (possibly partial) tile along x and y
         // must still contain them, otherwise the per-point kernel takes the plan
         const int VEC = (int)(16 / es), HXh = ((R + VEC - 1) / VEC) * VEC, TB = 2 * R + 2;
-        const int TX = mid ? 32 * VEC : 32 * VEC * 8 * cfg->py, TY = 8 * cfg->py;
+        const int TX = mid ? 32 * VEC : 32 * VEC * cfg->nwy * cfg->py, TY = cfg->nwy * cfg->py;
         const long long nx = plan->dims[0], ny = mid ? plan->dims[1] : 1;
         const int wlast = (int)((nx - 1) % TX) + 1, hlast = (int)((ny - 1) % TY) + 1;
         const int Kx = plan->bc[0].d.K_r, Ky = mid ? plan->bc[1].d.K_r : 0;
@@ -193,10 +195,13 @@ int32_t launch_star(const deo_plan* plan, void* du, const void* u, long long z0,
     const int VEC = (int)(16 / es);
     const int HX = ((C.R + VEC - 1) / VEC) * VEC;
     cuuint32_t box[3];
-    if (mid) { box[0] = (cuuint32_t)(32 * VEC + 2 * HX); box[1] = (cuuint32_t)(8 * C.py + 2 * C.R); box[2] = 1; }
+    if (mid) { box[0] = (cuuint32_t)(32 * VEC + 2 * HX); box[1] = (cuuint32_t)(C.nwy * C.py + 2 * C.R); box[2] = 1; }
     else { box[0] = 256; box[1] = 1; box[2] = 1; }
+    static const int promo_env = getenv("DEO_TMA_L2PROMO") ? atoi(getenv("DEO_TMA_L2PROMO")) : 3;
+    const CUtensorMapL2promotion promo = promo_env == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo_env == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                         : promo_env == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     CUresult r = enc(&C.tmap, es == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(u), dims,
-                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return DEO_ERR_CUDA; }
     if (!mid) { z0 = 0; z1 = plan->local_dim(plan->ndims - 1); }   // 2-D arrays stream along their last axis

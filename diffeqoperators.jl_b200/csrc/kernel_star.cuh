@@ -21,6 +21,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "generic_device.cuh"
 
 namespace deo {
@@ -51,7 +53,8 @@ struct StarConfig {
     std::vector<unsigned char> params;
     int R = 0;
     bool mid = false;
-    int py = 4;              // rows (or x segments) per thread: 4 -> one CTA per SM, 2 -> two CTAs per SM
+    int py = 2;              // rows (or x segments) per thread
+    int nwy = 8;             // warps per CTA (tile rows = nwy * py)
     int mask = 0;            // bit a: an operator acts along kernel axis a (x, mid, march)
     int zchunk_pref = 0;
     int sm_count = 0;
@@ -78,6 +81,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "bra LAB_WAIT;\n"
         "DONE:\n"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+// calls f(false_type, Face, integral_constant<int, 0>) ... f(false_type, Face, integral_constant<int, N-1>)
+template <int N, class Face, int U = 0, class F>
+__device__ __forceinline__ void unroll_steps(F& f) {
+    if constexpr (U < N) {
+        f(std::false_type{}, Face{}, std::integral_constant<int, U>{});
+        unroll_steps<N, Face, U + 1>(f);
+    }
 }
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
     asm volatile(
@@ -119,8 +144,12 @@ struct StarGeom {
     static constexpr int NBOX = MID ? 1 : (PITCH + BOXW - 1) / BOXW;
     static constexpr int PLANE = MID ? PITCH * ROWS : NBOX * BOXW;   // elements written per plane
     static constexpr int PLANE_BYTES = ((PLANE * (int)sizeof(T) + 127) / 128) * 128;
-    static constexpr int NS_WANT = R + 6;                         // ring: planes z..z+R live, 4 in flight, 1 being drained
-    static constexpr int NS_FIT = ((PY <= 2 ? 110 : 220) * 1024) / PLANE_BYTES;   // PY <= 2 variants run two CTAs per SM
+#ifndef DEO_STAR_AHEAD
+#define DEO_STAR_AHEAD 4
+#endif
+    static constexpr int NS_WANT = R + 2 + DEO_STAR_AHEAD;        // ring: planes z..z+R live, AHEAD in flight, 1 being drained
+    static constexpr int CTAS_PER_SM = (PY <= 2 && NWY <= 8) ? 2 : 1;
+    static constexpr int NS_FIT = ((CTAS_PER_SM == 2 ? 110 : 220) * 1024) / PLANE_BYTES;
     static constexpr int NS = NS_WANT < NS_FIT ? NS_WANT : NS_FIT;
     static constexpr int NQ = 2 * R + 1;
     static constexpr int THREADS = NWY * 32;
@@ -155,7 +184,7 @@ __device__ __forceinline__ void load_x_halo(const T* own, T (&xw)[Vec<T>::N + 2 
 }
 
 template <typename T, int R, int PY, int NWY, bool MID, int MASK>
-__global__ void __launch_bounds__(NWY * 32, (PY <= 2 ? 2 : 1))
+__global__ void __launch_bounds__(NWY * 32, ((PY <= 2 && NWY <= 8) ? 2 : 1))
 k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarParams<T, R> S,
        const T* __restrict__ u, T* __restrict__ du, int z_begin, int z_end, int zchunk) {
     using G = StarGeom<T, R, PY, NWY, MID>;
@@ -194,11 +223,10 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
                 tma_load_3d(dst + b * G::BOXW, &tmap, &full[slot], tx0 - HX + b * G::BOXW, 0, pz);
         }
     };
-    int k_issue = 0;
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NWY); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (; k_issue < NS && k_issue < n_planes; ++k_issue) issue_plane(k_issue);
+        for (int k0 = 0; k0 < NS && k0 < n_planes; ++k0) issue_plane(k0);
     }
     __syncthreads();
 
@@ -237,34 +265,59 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
 #pragma unroll
             for (int t = 0; t < NQ; ++t) zq[j][v][t] = T(0);
 
-    int ka = 0;                                            // ring index of the plane acquired in this step
-#pragma unroll 1
-    for (int z = zc0 - 2 * R; z < zc1; ++z, ++ka) {        // z = centre plane of this step (local index)
-        // --- acquire plane z+R: shift the queue, append this thread's values --------------------------
+    bool all_live = true;
+#pragma unroll
+    for (int j = 0; j < PY; ++j) all_live = all_live && live[j];
+    // CTA-uniform: a tile that touches no x/y face and lies fully inside the array runs the plain step
+    const bool cta_plain = !(xlo_tile || xhi_tile || ylo_tile || yhi_tile) && __syncthreads_and(all_live ? 1 : 0);
+
+    // One step = acquire plane z+R, compute and store centre plane z.  EDGE = false is the steady-state body with
+    // no boundary logic at all; EDGE = true adds priming, face tiles, partial tiles and the march-axis faces.
+    // ring state, advanced once per step: slot/parity of the plane being acquired, slot of the centre plane
+    int slot_a = 0, par_a = 0, slot_c = NS - R;           // slot_c trails slot_a by R (mod NS); meaningful once z >= zc0
+    int z = zc0 - 2 * R, ka = 0;                           // centre plane of the current step (local index), its acquire index
+    T* ocur[PY];                                           // output pointer of each vector at the centre plane of the current step
+#pragma unroll
+    for (int j = 0; j < PY; ++j) ocur[j] = optr[j] - (long long)(2 * R) * S.osz;
+    const uint32_t full_u32 = smem_u32(full), empty_u32 = smem_u32(empty);
+
+    // ROT < 0: the queue is shifted every step (zq[t] = plane z-R+t).  ROT = u >= 0 (plain steps, unrolled NQ times):
+    // the queue rotates by renaming instead: the new plane overwrites physical slot u, logical tap t lives in
+    // physical slot (u + 1 + t) % NQ; after NQ such steps the layout is the shifted one again.
+    // ZEDGE: priming / chunk-end / march-axis-face logic (shift mode only).  FACE: the tile touches an x or y face or is
+    // partial: x/y fix-up blocks and predicated stores.
+    auto step = [&](auto zedge_tag, auto face_tag, auto rot_tag) {
+        constexpr bool EDGE = decltype(zedge_tag)::value;
+        constexpr bool FACE = decltype(face_tag)::value;
+        constexpr int ROT = decltype(rot_tag)::value;
+        auto P = [](int t) constexpr { return ROT < 0 ? t : (ROT + 1 + t) % NQ; };
+        // --- acquire plane z+R ------------------------------------------------------------------------
         {
-            const int slot_new = ka % NS;
-            mbar_wait(&full[slot_new], (ka / NS) & 1);
-            const T* pn = planes + (size_t)slot_new * PLANE_ELEMS;
+            mbar_wait_u32(full_u32 + 8u * slot_a, par_a);
+            const T* pn = planes + slot_a * PLANE_ELEMS;
 #pragma unroll
             for (int j = 0; j < PY; ++j) {
                 T val[VEC];
                 ld_vec<T, VEC>(pn + soff[j], val);
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) {
+                    if constexpr (ROT < 0) {
 #pragma unroll
-                    for (int t = 0; t < NQ - 1; ++t) zq[j][v][t] = zq[j][v][t + 1];
-                    zq[j][v][NQ - 1] = val[v];
+                        for (int t = 0; t < NQ - 1; ++t) zq[j][v][t] = zq[j][v][t + 1];
+                        zq[j][v][NQ - 1] = val[v];
+                    } else {
+                        zq[j][v][ROT] = val[v];
+                    }
                 }
             }
-            if (ka < R) {                                  // planes below the chunk only feed the queue: free the slot now
+            if (EDGE && (ka < R || ka >= n_planes - R)) {  // planes outside the chunk only feed the queue: free the slot now
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[slot_new]);
+                if (lane == 0) mbar_arrive_u32(empty_u32 + 8u * slot_a);
             }
         }
-        if (z >= zc0) {
+        if (!EDGE || z >= zc0) {
             // --- centre plane z ------------------------------------------------------------------------
-            const int kc = ka - R;                         // its ring index
-            const T* pl = planes + (size_t)(kc % NS) * PLANE_ELEMS;
+            const T* pl = planes + slot_c * PLANE_ELEMS;
             const int gz = z + S.row0_z;
             T tot[PY][VEC];
             // ================= x operator: window = [R halo | VEC own (already in the queue) | R halo] =================
@@ -274,7 +327,7 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
                     T xw[XW];
                     load_x_halo<T, R>(pl + soff[j], xw);
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) xw[R + v] = zq[j][v][R];
+                    for (int v = 0; v < VEC; ++v) xw[R + v] = zq[j][v][P(R)];
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) {
                         T a = T(0);
@@ -284,7 +337,7 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
                     }
                 }
                 // rows whose stencil touches the x ghost (x < ex, x >= nx - ex): full row sums from the tile, in q order
-                if (xlo_tile || xhi_tile) {
+                if (FACE && (xlo_tile || xhi_tile)) {
                     if constexpr (MID) {
                         // cooperative: lane e computes one whole row sum, the owner lane picks it up by shuffle
                         constexpr int NE = PY * R;         // items per face: (tile row jj, edge row r)
@@ -300,26 +353,29 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
 #pragma unroll 1
                             for (int k = 0; k < K; ++k) g = fma_t(a[k], arow[k], g);
                             g += side ? S.b_r[0] : S.b_l[0];
-                            if (!side) {                   // q[0] = low ghost, q[k] = u[k-1]
-                                res = fma_t(w[0], g, T(0));
-#pragma unroll 1
-                                for (int k = 1; k < TB; ++k) res = fma_t(w[k], row[k - 1], res);
-                            } else {                       // q[n+2-TB+k] = u[n+1-TB+k], last tap = high ghost
-#pragma unroll 1
-                                for (int k = 0; k < TB - 1; ++k) res = fma_t(w[k], row[nx + 1 - TB + k], res);
-                                res = fma_t(w[TB - 1], g, res);
-                            }
+                            // all taps are loaded first (independent shared-memory loads), then summed in q order
+                            T q[TB];
+                            const T* qrow = side ? row + (nx + 1 - TB) : row - 1;   // qrow[k] = q[k] (low) / q[n+2-TB+k] (high)
+#pragma unroll
+                            for (int k = 0; k < TB; ++k) q[k] = ((!side && k == 0) || (side && k == TB - 1)) ? g : qrow[k];
+#pragma unroll
+                            for (int k = 0; k < TB; ++k) res = fma_t(w[k], q[k], res);
                         }
+                        // owners: global x = i (low face) / nx-ex+i (high face), i < ex <= R; row j of this warp
 #pragma unroll
                         for (int j = 0; j < PY; ++j) {
 #pragma unroll
-                            for (int v = 0; v < VEC; ++v) {
-                                const int xg = gx[j] + v;
-                                const bool lo = xlo_tile && xg < ex;
-                                const bool hi = xhi_tile && xg >= nx - ex && xg < nx;
-                                const int e = lo ? j * R + xg : (hi ? NE + j * R + (xg - (nx - ex)) : 0);
-                                const T val = __shfl_sync(FULL, res, e);
-                                if (lo || hi) tot[j][v] = val;
+                            for (int i = 0; i < R; ++i) {
+                                if (xlo_tile) {            // CTA-uniform
+                                    const T val = __shfl_sync(FULL, res, j * R + i);
+#pragma unroll
+                                    for (int v = 0; v < VEC; ++v) if (i < ex && gx[j] + v == i) tot[j][v] = val;
+                                }
+                                if (xhi_tile) {
+                                    const T val = __shfl_sync(FULL, res, NE + j * R + i);
+#pragma unroll
+                                    for (int v = 0; v < VEC; ++v) if (i < ex && gx[j] + v == nx - ex + i) tot[j][v] = val;
+                                }
                             }
                         }
                     } else {
@@ -363,7 +419,7 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
                     T row[VEC];
                     if (r >= R && r < R + PY) {
 #pragma unroll
-                        for (int v = 0; v < VEC; ++v) row[v] = zq[r - R][v][R];
+                        for (int v = 0; v < VEC; ++v) row[v] = zq[r - R][v][P(R)];
                     } else {
                         ld_vec<T, VEC>(pl + soff[0] + (r - R) * PITCH, row);
                     }
@@ -377,7 +433,7 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
                     }
                 }
                 // rows whose stencil touches the y ghost: warp-uniform (a tile row belongs to one warp)
-                if (ylo_tile || yhi_tile) {
+                if (FACE && (ylo_tile || yhi_tile)) {
                     const T* colbase = pl + (R - ty0) * PITCH + HX + lane * VEC;   // colbase[y*PITCH + v] = value at global row y
 #pragma unroll
                     for (int j = 0; j < PY; ++j) {
@@ -399,18 +455,22 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
                         }
 #pragma unroll
                         for (int v = 0; v < VEC; ++v) g[v] += hi ? S.b_r[1] : S.b_l[1];
-#pragma unroll 1
-                        for (int k = 0; k < TB; ++k) {
-                            const int c = hi ? ny + 1 - TB + k : k - 1;
-                            T val[VEC];
-                            if (c == -1 || c == ny) {
+                        {
+                            const T* qcol = colbase + (hi ? ny + 1 - TB : -1) * PITCH;   // qcol[k*PITCH] = q[k] / q[n+2-TB+k]
+                            T q[TB][VEC];
 #pragma unroll
-                                for (int v = 0; v < VEC; ++v) val[v] = g[v];
-                            } else {
-                                ld_vec<T, VEC>(colbase + c * PITCH, val);
+                            for (int k = 0; k < TB; ++k) {
+                                if ((!hi && k == 0) || (hi && k == TB - 1)) {
+#pragma unroll
+                                    for (int v = 0; v < VEC; ++v) q[k][v] = g[v];
+                                } else {
+                                    ld_vec<T, VEC>(qcol + k * PITCH, q[k]);
+                                }
                             }
 #pragma unroll
-                            for (int v = 0; v < VEC; ++v) res[v] = fma_t(w[k], val[v], res[v]);
+                            for (int k = 0; k < TB; ++k)
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v) res[v] = fma_t(w[k], q[k][v], res[v]);
                         }
 #pragma unroll
                         for (int v = 0; v < VEC; ++v) acc[j][v] = res[v];
@@ -424,7 +484,7 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
             // ================= march-axis operator from the register queue =================
             // rows whose stencil touches a march-axis ghost take their term from du (see below)
             if constexpr (has_z) {
-                const bool z_low_edge = gz < ez, z_high_edge = gz >= S.nglob_z - ez;
+                const bool z_low_edge = EDGE && gz < ez, z_high_edge = EDGE && gz >= S.nglob_z - ez;
                 if (!(z_low_edge || z_high_edge)) {
 #pragma unroll
                     for (int j = 0; j < PY; ++j) {
@@ -432,7 +492,7 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
                         for (int v = 0; v < VEC; ++v) {
                             T s = T(0);
 #pragma unroll
-                            for (int t = 0; t < NQ; ++t) s = fma_t(S.w[2][t], zq[j][v][t], s);
+                            for (int t = 0; t < NQ; ++t) s = fma_t(S.w[2][t], zq[j][v][P(t)], s);
                             tot[j][v] = (has_x || has_y) ? tot[j][v] + s : s;
                         }
                     }
@@ -442,7 +502,7 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
                         T a[VEC];
 #pragma unroll
                         for (int v = 0; v < VEC; ++v) a[v] = T(0);
-                        if (live[j]) ld_vec<T, VEC>(optr[j] + (long long)(z - zc0) * S.osz, a);
+                        if (live[j]) ld_vec<T, VEC>(ocur[j], a);
 #pragma unroll
                         for (int v = 0; v < VEC; ++v) tot[j][v] = (has_x || has_y) ? tot[j][v] + a[v] : a[v];
                     }
@@ -455,17 +515,17 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
             }
             // release the centre plane's slot, then store
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[kc % NS]);
+            if (lane == 0) mbar_arrive_u32(empty_u32 + 8u * slot_c);
 #pragma unroll
             for (int j = 0; j < PY; ++j)
-                if (live[j]) st_vec<T, VEC>(optr[j] + (long long)(z - zc0) * S.osz, tot[j]);
+                if (!FACE || live[j]) st_vec<T, VEC>(ocur[j], tot[j]);
 
             if constexpr (has_z) {
                 // --- march-axis rows that touch a ghost, from the register queue -------------------------------
                 // low rows r < ez need q[0..TB-1] = ghost, planes 0..2R: exactly the queue when the centre is global plane R.
                 // Their x/y part is already in du (stored above at the steps gz = r); add the march-axis term now (it is
                 // the last operator, so the association matches the reference's sum).
-                if (gz == R && ez > 0) {
+                if (EDGE && gz == R && ez > 0) {
 #pragma unroll
                     for (int j = 0; j < PY; ++j) {
                         if (!live[j]) continue;
@@ -479,7 +539,7 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
                         }
 #pragma unroll 1
                         for (int r = 0; r < ez; ++r) {
-                            T* dst = optr[j] + (long long)(r - S.row0_z - zc0) * S.osz;
+                            T* dst = ocur[j] + (long long)(r - S.row0_z - z) * S.osz;
                             T old[VEC];
                             ld_vec<T, VEC>(dst, old);
 #pragma unroll
@@ -495,7 +555,7 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
                 }
                 // high rows need planes n-1-2R..n-1 and the high ghost: the queue when the centre is global plane n-1-R.
                 // Their term is parked in du now and picked up (tot + du) when those rows are computed a few steps later.
-                if (gz == S.nglob_z - 1 - R && ez > 0) {
+                if (EDGE && gz == S.nglob_z - 1 - R && ez > 0) {
 #pragma unroll
                     for (int j = 0; j < PY; ++j) {
                         if (!live[j]) continue;
@@ -509,7 +569,7 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
                         }
 #pragma unroll 1
                         for (int r = 0; r < ez; ++r) {
-                            T* dst = optr[j] + (long long)(S.nglob_z - ez + r - S.row0_z - zc0) * S.osz;
+                            T* dst = ocur[j] + (long long)(S.nglob_z - ez + r - S.row0_z - z) * S.osz;
                             T out[VEC];
 #pragma unroll
                             for (int v = 0; v < VEC; ++v) {
@@ -524,17 +584,43 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
                 }
             }
         }
-        // --- producer: refill the slot drained one step ago (all warps have normally released it by now) ----
-        if (threadIdx.x == 0) {
-            const int kc_done = ka - R;                    // ring index of the centre just released by this warp (< 0 while priming)
-            while (k_issue < n_planes && k_issue - NS <= kc_done - 1) {
-                const int slot = k_issue % NS;
-                mbar_wait(&empty[slot], ((k_issue / NS) - 1) & 1);
-                issue_plane(k_issue);
-                ++k_issue;
+        // --- producer (thread 0): after step ka, plane ka-R-1+NS can reuse the slot of the previous centre (ring index
+        // ka-R-1), which every warp released when it finished step ka-1
+        {
+            const int p = ka - R - 1 + NS;
+            if (threadIdx.x == 0 && ka >= R + 1 && p < n_planes) {
+                mbar_wait(&empty[p % NS], ((p / NS) - 1) & 1);
+                issue_plane(p);
             }
         }
+        // --- advance the ring and the output pointers ---------------------------------------------------
+        ++z; ++ka;
+        if (++slot_a == NS) { slot_a = 0; par_a ^= 1; }
+        if (++slot_c == NS) slot_c = 0;
+#pragma unroll
+        for (int j = 0; j < PY; ++j) ocur[j] += S.osz;
+    };
+
+    // steps whose centre is a plain plane: computed (z >= zc0), its acquired plane still inside the chunk, and, when a
+    // march-axis operator exists, strictly inside (R, n-1-R) in global planes so that no ghost term is read, parked
+    // or added in that step
+    int zp0 = zc0, zp1 = zc1 - R;
+    if constexpr (has_z) {
+        zp0 = max(zp0, R + 1 - S.row0_z);
+        zp1 = min(zp1, S.nglob_z - 1 - R - S.row0_z);
     }
+    using Shift = std::integral_constant<int, -1>;
+#pragma unroll 1
+    while (z < zc1 && z < zp0) step(std::true_type{}, std::true_type{}, Shift{});
+    if (cta_plain) {
+#pragma unroll 1
+        while (z + NQ <= zp1) unroll_steps<NQ, std::false_type>(step);   // NQ steps per trip: the queue rotates by renaming
+    } else {
+#pragma unroll 1
+        while (z < zp1) step(std::false_type{}, std::true_type{}, Shift{});   // face / partial tiles: x/y fix-ups, no z-edge logic
+    }
+#pragma unroll 1
+    while (z < zc1) step(std::true_type{}, std::true_type{}, Shift{});
 }
 
 template <typename T, int R, int PY, int NWY, bool MID, int MASK>
@@ -563,7 +649,7 @@ int32_t launch_variant(const StarConfig& C, const void* u, void* du, long long z
             const long long last = len - (nchunks - 1) * c;
             if (nchunks > 1 && last < R + 1) continue;
             const long long ctas = tiles * nchunks;
-            const long long slots = (long long)C.sm_count * (PY <= 2 ? 2 : 1);
+            const long long slots = (long long)C.sm_count * G::CTAS_PER_SM;
             const long long waves = (ctas + slots - 1) / slots;
             const double cost = (double)waves * (double)(c + 2 * R);   // makespan in plane-steps (each CTA also primes 2R planes)
             if (cost < best - 1e-12) { best = cost; best_zc = c; }
@@ -582,32 +668,36 @@ int32_t launch_variant(const StarConfig& C, const void* u, void* du, long long z
 template <typename T, int R>
 int32_t star_launch_R(const StarConfig& C, const void* u, void* du, long long z0, long long z1, cudaStream_t s);
 
-template <typename T, int R, int PY, bool MID>
+template <typename T, int R, int PY, int NWY, bool MID>
 int32_t star_launch_mask(const StarConfig& C, const void* u, void* du, long long z0, long long z1, cudaStream_t s) {
     switch (C.mask) {
-        case 1: return launch_variant<T, R, PY, 8, MID, 1>(C, u, du, z0, z1, s);
-        case 4: return launch_variant<T, R, PY, 8, MID, 4>(C, u, du, z0, z1, s);
-        case 5: return launch_variant<T, R, PY, 8, MID, 5>(C, u, du, z0, z1, s);
+        case 1: return launch_variant<T, R, PY, NWY, MID, 1>(C, u, du, z0, z1, s);
+        case 4: return launch_variant<T, R, PY, NWY, MID, 4>(C, u, du, z0, z1, s);
+        case 5: return launch_variant<T, R, PY, NWY, MID, 5>(C, u, du, z0, z1, s);
     }
     if constexpr (MID) {
         switch (C.mask) {
-            case 2: return launch_variant<T, R, PY, 8, MID, 2>(C, u, du, z0, z1, s);
-            case 3: return launch_variant<T, R, PY, 8, MID, 3>(C, u, du, z0, z1, s);
-            case 6: return launch_variant<T, R, PY, 8, MID, 6>(C, u, du, z0, z1, s);
-            case 7: return launch_variant<T, R, PY, 8, MID, 7>(C, u, du, z0, z1, s);
+            case 2: return launch_variant<T, R, PY, NWY, MID, 2>(C, u, du, z0, z1, s);
+            case 3: return launch_variant<T, R, PY, NWY, MID, 3>(C, u, du, z0, z1, s);
+            case 6: return launch_variant<T, R, PY, NWY, MID, 6>(C, u, du, z0, z1, s);
+            case 7: return launch_variant<T, R, PY, NWY, MID, 7>(C, u, du, z0, z1, s);
         }
     }
     set_error("star kernel: unsupported operator mask %d", C.mask);
     return DEO_ERR_UNSUPPORTED;
 }
 
+template <typename T, int R, int PY, int NWY>
+int32_t star_launch_mid(const StarConfig& C, const void* u, void* du, long long z0, long long z1, cudaStream_t s) {
+    return C.mid ? star_launch_mask<T, R, PY, NWY, true>(C, u, du, z0, z1, s) : star_launch_mask<T, R, PY, NWY, false>(C, u, du, z0, z1, s);
+}
+
 #define DEO_STAR_INSTANTIATE(R_)                                                                                              \
     template <typename T, int R>                                                                                              \
     int32_t star_launch_R(const StarConfig& C, const void* u, void* du, long long z0, long long z1, cudaStream_t s) {        \
-        if (C.py == 2) return C.mid ? star_launch_mask<T, R, 2, true>(C, u, du, z0, z1, s)                                    \
-                                    : star_launch_mask<T, R, 2, false>(C, u, du, z0, z1, s);                                  \
-        return C.mid ? star_launch_mask<T, R, 4, true>(C, u, du, z0, z1, s)                                                   \
-                     : star_launch_mask<T, R, 4, false>(C, u, du, z0, z1, s);                                                 \
+        if (C.py == 2 && C.nwy == 16) return star_launch_mid<T, R, 2, 16>(C, u, du, z0, z1, s);                              \
+        if (C.py == 2) return star_launch_mid<T, R, 2, 8>(C, u, du, z0, z1, s);                                               \
+        return star_launch_mid<T, R, 4, 8>(C, u, du, z0, z1, s);                                                              \
     }                                                                                                                          \
     template int32_t star_launch_R<double, R_>(const StarConfig&, const void*, void*, long long, long long, cudaStream_t);    \
     template int32_t star_launch_R<float, R_>(const StarConfig&, const void*, void*, long long, long long, cudaStream_t);
