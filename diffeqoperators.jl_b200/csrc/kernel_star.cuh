@@ -21,6 +21,7 @@
 #pragma once
 #include <cuda.h>
 
+#include <cstdlib>
 #include <type_traits>
 
 #include "generic_device.cuh"
@@ -627,7 +628,7 @@ template <typename T, int R, int PY, int NWY, bool MID, int MASK>
 int32_t launch_variant(const StarConfig& C, const void* u, void* du, long long z0, long long z1, cudaStream_t s) {
     using G = StarGeom<T, R, PY, NWY, MID>;
     const StarParams<T, R>& S = *reinterpret_cast<const StarParams<T, R>*>(C.params.data());
-    static bool attr_set = false;
+    static bool attr_set = false, attr_set2 = false;
     auto kern = k_star<T, R, PY, NWY, MID, MASK>;
     if (!attr_set) {
         DEO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
@@ -658,7 +659,12 @@ int32_t launch_variant(const StarConfig& C, const void* u, void* du, long long z
         zc = best_zc;
     }
     dim3 grid((unsigned)((S.nx + G::TX - 1) / G::TX), (unsigned)(MID ? (S.ny + G::TY - 1) / G::TY : 1), (unsigned)((len + zc - 1) / zc));
-    kern<<<grid, G::THREADS, G::SMEM, s>>>(map, S, (const T*)u, (T*)du, (int)z0, (int)z1, (int)zc);
+    static const size_t extra_smem = getenv("DEO_STAR_EXTRA_SMEM") ? (size_t)atoll(getenv("DEO_STAR_EXTRA_SMEM")) : 0;   // occupancy experiments
+    if (extra_smem && !attr_set2) {
+        DEO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(G::SMEM + extra_smem)));
+        attr_set2 = true;
+    }
+    kern<<<grid, G::THREADS, G::SMEM + extra_smem, s>>>(map, S, (const T*)u, (T*)du, (int)z0, (int)z1, (int)zc);
     DEO_CUDA(cudaGetLastError());
     return DEO_OK;
 }
