@@ -172,6 +172,8 @@ int32_t star_configure(deo_plan* plan) {
         if (mid && (cfg->mask & 2) && (hlast + R < TB - 1 || hlast + R < Ky || ny < TB)) return DEO_OK;
     }
     cfg->zchunk_pref = 64;
+    cfg->zchunk_max = getenv("DEO_STAR_ZCHUNK") ? atoi(getenv("DEO_STAR_ZCHUNK")) : 64;
+    cfg->l2promo = getenv("DEO_TMA_L2PROMO") ? atoi(getenv("DEO_TMA_L2PROMO")) : 3;
     plan->star = cfg;
     plan->kernel = "star";
     return DEO_OK;
@@ -197,7 +199,7 @@ int32_t launch_star(const deo_plan* plan, void* du, const void* u, long long z0,
     cuuint32_t box[3];
     if (mid) { box[0] = (cuuint32_t)(32 * VEC + 2 * HX); box[1] = (cuuint32_t)(C.nwy * C.py + 2 * C.R); box[2] = 1; }
     else { box[0] = 256; box[1] = 1; box[2] = 1; }
-    static const int promo_env = getenv("DEO_TMA_L2PROMO") ? atoi(getenv("DEO_TMA_L2PROMO")) : 3;
+    const int promo_env = C.l2promo;
     const CUtensorMapL2promotion promo = promo_env == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo_env == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
                                          : promo_env == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     CUresult r = enc(&C.tmap, es == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(u), dims,

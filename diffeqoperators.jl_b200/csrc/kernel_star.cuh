@@ -58,6 +58,8 @@ struct StarConfig {
     int nwy = 8;             // warps per CTA (tile rows = nwy * py)
     int mask = 0;            // bit a: an operator acts along kernel axis a (x, mid, march)
     int zchunk_pref = 0;
+    int zchunk_max = 0;      // experiments (DEO_STAR_ZCHUNK): upper bound on the planes per CTA along the march axis
+    int l2promo = 3;         // CUtensorMapL2promotion of the tensor map (DEO_TMA_L2PROMO)
     int sm_count = 0;
 };
 
@@ -646,6 +648,7 @@ int32_t launch_variant(const StarConfig& C, const void* u, void* du, long long z
         for (long long nch = 1; nch <= len; ++nch) {
             long long c = (len + nch - 1) / nch;
             if (c < 4 * R + 4 && nch > 1) break;
+            if (C.zchunk_max > 0 && c > C.zchunk_max && c > 4 * R + 4) continue;
             const long long nchunks = (len + c - 1) / c;
             const long long last = len - (nchunks - 1) * c;
             if (nchunks > 1 && last < R + 1) continue;
@@ -654,7 +657,7 @@ int32_t launch_variant(const StarConfig& C, const void* u, void* du, long long z
             const long long waves = (ctas + slots - 1) / slots;
             const double cost = (double)waves * (double)(c + 2 * R);   // makespan in plane-steps (each CTA also primes 2R planes)
             if (cost < best - 1e-12) { best = cost; best_zc = c; }
-            if (ctas > 64LL * C.sm_count) break;
+            if (ctas > 64LL * C.sm_count && C.zchunk_max == 0) break;
         }
         zc = best_zc;
     }

@@ -107,3 +107,90 @@ class SlabPlan(Plan):
         ms = C.c_float(0)
         _lib.check(_lib.load().deo_dist_plan_time(self._h, du._h, u_ext._h, reps, C.byref(ms)))
         return float(ms.value)
+
+
+# ---- host-side scatter / gather over the host runtime's process group (no arithmetic) ---------------------
+def _np_to_torch(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a.reshape(-1, order="F")))
+
+
+def broadcast_unique_id():
+    """Rank 0 creates the NCCL unique id, every rank returns the same 128 bytes (any torch backend)."""
+    import torch
+    import torch.distributed as dist
+    backend = dist.get_backend()
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    t = torch.zeros(_lib.DEO_DIST_ID_BYTES, dtype=torch.uint8, device=dev)
+    if dist.get_rank() == 0:
+        t.copy_(torch.frombuffer(bytearray(SlabContext.new_unique_id()), dtype=torch.uint8))
+    dist.broadcast(t, src=0)
+    return bytes(t.cpu().numpy().tobytes())
+
+
+def scatter_slabs(u_global, global_shape, dtype, halo: int, fill=0.0):
+    """deo_dist_scatter of the proposed ABI, done by the host runtime: rank 0 holds `u_global`; every rank
+    returns its [halo | own planes | halo] host block with the halo planes already filled from the
+    neighbouring slabs (physical faces get `fill`, they are never read)."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dtype = np.dtype(dtype)
+    plane = int(np.prod(global_shape[:-1], dtype=np.int64))
+    s, c = slab_bounds(global_shape[-1], world, rank)
+    mine = torch.empty(plane * (c + 2 * halo), dtype=torch.from_numpy(np.empty(0, dtype)).dtype)
+    if rank == 0:
+        for r in range(world):
+            ext = extended_slab(np.asarray(u_global, dtype=dtype), r, world, halo, fill=fill)
+            t = _np_to_torch(ext)
+            if r == 0:
+                mine.copy_(t)
+            else:
+                dist.send(t, dst=r)
+    else:
+        dist.recv(mine, src=0)
+    return mine.numpy().reshape(tuple(global_shape[:-1]) + (c + 2 * halo,), order="F")
+
+
+def gather_slabs(du_local, global_shape):
+    """deo_dist_gather: rank 0 returns the reassembled global array, the other ranks None."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if rank != 0:
+        dist.send(_np_to_torch(du_local), dst=0)
+        return None
+    out = np.empty(tuple(global_shape), dtype=du_local.dtype, order="F")
+    plane = int(np.prod(global_shape[:-1], dtype=np.int64))
+    for r in range(world):
+        s, c = slab_bounds(global_shape[-1], world, r)
+        if r == 0:
+            out[..., s:s + c] = du_local
+        else:
+            t = torch.empty(plane * c, dtype=_np_to_torch(du_local).dtype)
+            dist.recv(t, src=r)
+            out[..., s:s + c] = t.numpy().reshape(tuple(global_shape[:-1]) + (c,), order="F")
+    return out
+
+
+def exchange_halos_host(ext, halo: int):
+    """The library's exchange protocol (dist.cu: send my first/last `halo` own planes, receive into my
+    halo planes) replayed on host arrays over the process group -- used by the CPU tests of the N>1 path."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    cnt = ext.shape[-1] - 2 * halo
+    reqs, bufs = [], []
+    for nb, send_sl, recv_sl in ((rank - 1, slice(halo, 2 * halo), slice(0, halo)),
+                                 (rank + 1, slice(cnt, cnt + halo), slice(cnt + halo, cnt + 2 * halo))):
+        if nb < 0 or nb >= world or halo == 0:
+            continue
+        st = _np_to_torch(ext[..., send_sl])
+        rt = torch.empty_like(st)
+        reqs += [dist.isend(st, dst=nb), dist.irecv(rt, src=nb)]
+        bufs.append((recv_sl, rt))
+    for r in reqs:
+        r.wait()
+    for sl, rt in bufs:
+        ext[..., sl] = rt.numpy().reshape(ext[..., sl].shape, order="F")
+    return ext
