@@ -182,6 +182,8 @@ struct deo_plan {
 namespace deo {
 // plan_build.cu
 int32_t build_device_plan(deo_plan* plan);
+struct HostRow { int start = 0, ntaps = 0; double w[kMaxBTaps]; };   // row r = sum_k w[k] * q[start + k]
+int32_t plan_all_rows(const deo_plan* plan, int op_index, std::vector<HostRow>& rows);
 // kernel_generic.cu : computes local output planes [z0, z1) of the last axis (whole array when ndims<3 uses z in [0,1))
 int32_t launch_generic(const deo_plan* plan, void* du, const void* u, long long z0, long long z1, cudaStream_t s);
 // kernel_star.cu

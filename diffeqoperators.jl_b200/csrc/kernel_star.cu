@@ -115,6 +115,124 @@ bool fill_params(const deo_plan* plan, const int kaxis_of_plan_axis[3], bool mid
     return true;
 }
 
+
+// ---- merged per-row tables (TABLE variants) ------------------------------------------------------------------
+// Every operator is linear in the same ghost-padded pencil, so all operators acting along one axis fold into ONE
+// per-row stencil: W_a[r][t] = sum_ops (c*w)_op,r placed on the common window q[r+1-R .. r+1+R].  That covers
+// non-uniform grids (per-row Fornberg weights), coefficient vectors, upwind operators (the wind direction of row r
+// is known from sign(c[r]) when the plan is built or its coefficients are updated) and several operators per axis
+// in one pass.  The sum over operators is formed here in Float64 and rounded once to T, so the result differs from
+// the reference's operator-by-operator sum by reassociation only (within the parity tolerance, not bitwise).
+struct AxisRows {
+    int n = 0;
+    std::vector<std::vector<HostRow>> ops;    // per operator on this axis: n rows
+};
+
+// smallest template radius R such that rows [R, n-R) fit q[r+1-R .. r+1+R] and the R rows at each face fit the
+// TB = 2R+2 taps nearest to it
+int table_radius(const AxisRows& A) {
+    for (int R = 1; R <= 4; ++R) {
+        const int TB = 2 * R + 2, n = A.n;
+        if (n < 4 * R + 4) return 0;
+        bool ok = true;
+        for (const auto& rows : A.ops) {
+            for (int r = 0; r < n && ok; ++r) {
+                const HostRow& h = rows[(size_t)r];
+                const int lo = h.start, hi = h.start + h.ntaps - 1;   // q indices
+                if (r < R) ok = hi <= TB - 1;
+                else if (r >= n - R) ok = lo >= n + 2 - TB;
+                else ok = lo >= r + 1 - R && hi <= r + 1 + R;
+            }
+            if (!ok) break;
+        }
+        if (ok) return R;
+    }
+    return 0;
+}
+
+template <typename T, int R>
+bool fill_params_table(deo_plan* plan, const AxisRows (&axes)[3], const int plan_axis_of_kaxis[3], bool mid, StarConfig& C) {
+    using SP = StarParams<T, R>;
+    constexpr int NQ = SP::NQ, TB = SP::TB;
+    const DevPlan<T>& P = *reinterpret_cast<const DevPlan<T>*>(plan->devplan.data());
+    C.params.assign(sizeof(SP), 0);
+    SP& S = *reinterpret_cast<SP*>(C.params.data());
+    const int march_plan_axis = plan->ndims - 1;
+    S.nx = P.n_out[0];
+    S.ny = mid ? P.n_out[1] : 1;
+    S.nz = P.n_out[march_plan_axis];
+    S.in_off_z = P.in_off[march_plan_axis];
+    S.row0_z = P.row0[march_plan_axis];
+    S.nglob_z = P.n_glob[march_plan_axis];
+    S.isy = mid ? P.in_stride[1] : 0;
+    S.osy = mid ? P.out_stride[1] : 0;
+    S.isz = P.in_stride[march_plan_axis];
+    S.osz = P.out_stride[march_plan_axis];
+    for (int ka = 0; ka < 3; ++ka) {
+        S.has[ka] = 0; S.opidx[ka] = -1; S.nedge[ka] = 0; S.K_l[ka] = S.K_r[ka] = 0; S.tab[ka] = nullptr;
+        const AxisRows& A = axes[ka];
+        if (A.ops.empty()) continue;
+        S.has[ka] = 1;
+        C.mask |= 1 << ka;
+        S.nedge[ka] = R;
+        const int n = A.n;
+        std::vector<double> tab((size_t)n * NQ, 0.0), lowrows((size_t)R * TB, 0.0), highrows((size_t)R * TB, 0.0);
+        for (const auto& rows : A.ops) {
+            for (int r = 0; r < n; ++r) {
+                const HostRow& h = rows[(size_t)r];
+                for (int k = 0; k < h.ntaps; ++k) {
+                    const int q = h.start + k;
+                    if (r < R) lowrows[(size_t)r * TB + q] += h.w[k];
+                    else if (r >= n - R) highrows[(size_t)(r - (n - R)) * TB + (q - (n + 2 - TB))] += h.w[k];
+                    else tab[(size_t)r * NQ + (q - (r + 1 - R))] += h.w[k];
+                }
+            }
+        }
+        for (int r = 0; r < R; ++r)
+            for (int k = 0; k < TB; ++k) {
+                S.bw[ka][0][r][k] = (T)lowrows[(size_t)r * TB + k];
+                S.bw[ka][1][r][k] = (T)highrows[(size_t)r * TB + k];
+            }
+        std::vector<T> tabT(tab.size());
+        for (size_t i = 0; i < tab.size(); ++i) tabT[i] = (T)tab[i];
+        auto blob = std::make_unique<DeviceBlob>();
+        if (cudaMalloc(&blob->p, tabT.size() * sizeof(T)) != cudaSuccess) return false;
+        blob->bytes = tabT.size() * sizeof(T);
+        if (cudaMemcpy(blob->p, tabT.data(), blob->bytes, cudaMemcpyHostToDevice) != cudaSuccess) return false;
+        S.tab[ka] = (const T*)blob->p;
+        plan->blobs.push_back(std::move(blob));
+        // boundary condition of this axis
+        const HostBC& H = plan->bc[plan_axis_of_kaxis[ka]];
+        if (H.d.kind != DEO_BC_AFFINE || H.d.per_face) return false;
+        const int Kmax = ka == 2 ? NQ : kStarMaxK;
+        if (H.d.K_l > Kmax || H.d.K_r > Kmax || H.d.K_l > kStarMaxK || H.d.K_r > kStarMaxK) return false;
+        S.K_l[ka] = H.d.K_l;
+        S.K_r[ka] = H.d.K_r;
+        const T* al = (const T*)H.a_l.data();
+        const T* ar = (const T*)H.a_r.data();
+        for (int t = 0; t < H.d.K_l; ++t) S.a_l[ka][t] = al[t];
+        for (int t = 0; t < H.d.K_r; ++t) S.a_r[ka][t] = ar[t];
+        S.b_l[ka] = *(const T*)H.b_l.data();
+        S.b_r[ka] = *(const T*)H.b_r.data();
+        if (ka == 2) {
+            for (int t = 0; t < H.d.K_l; ++t) S.azl_pad[t] = al[t];
+            for (int t = 0; t < H.d.K_r; ++t) S.azr_pad[NQ - H.d.K_r + t] = ar[t];
+        }
+    }
+    return true;
+}
+
+template <typename T>
+bool fill_params_table_R(deo_plan* plan, const AxisRows (&axes)[3], const int pax[3], bool mid, StarConfig& C) {
+    switch (C.R) {
+        case 1: return fill_params_table<T, 1>(plan, axes, pax, mid, C);
+        case 2: return fill_params_table<T, 2>(plan, axes, pax, mid, C);
+        case 3: return fill_params_table<T, 3>(plan, axes, pax, mid, C);
+        case 4: return fill_params_table<T, 4>(plan, axes, pax, mid, C);
+    }
+    return false;
+}
+
 template <typename T>
 bool fill_params_R(const deo_plan* plan, const int kaxis[3], bool mid, StarConfig& C) {
     switch (C.R) {
@@ -128,7 +246,25 @@ bool fill_params_R(const deo_plan* plan, const int kaxis[3], bool mid, StarConfi
 
 }  // namespace
 
+// The tile geometry must contain everything the x / y edge paths read (boundary stencils and BC stencils).
+static bool tile_fits(const deo_plan* plan, const StarConfig& cfg, bool mid) {
+    const size_t es = plan->elem();
+    const int R = cfg.R;
+    const int VEC = (int)(16 / es), HXh = ((R + VEC - 1) / VEC) * VEC, TB = 2 * R + 2;
+    const int TX = mid ? 32 * VEC : 32 * VEC * cfg.nwy * cfg.py, TY = cfg.nwy * cfg.py;
+    const long long nx = plan->dims[0], ny = mid ? plan->dims[1] : 1;
+    const int wlast = (int)((nx - 1) % TX) + 1, hlast = (int)((ny - 1) % TY) + 1;
+    const int Kx = plan->bc[0].d.K_r, Ky = mid ? plan->bc[1].d.K_r : 0;
+    if ((cfg.mask & 1) && (wlast + HXh < TB - 1 || wlast + HXh < Kx || nx < TB)) return false;
+    if (mid && (cfg.mask & 2) && (hlast + R < TB - 1 || hlast + R < Ky || ny < TB)) return false;
+    return true;
+}
+
 // Decides whether the plan can run on the tiled kernel; if so attaches a StarConfig to it.
+//   CONST variants: one uniform centered constant-coefficient operator per axis, in axis order -- weights in the constant
+//                   bank, arithmetic order identical to the per-point kernel (bitwise equal results);
+//   TABLE variants: anything else that is a sum of 1-D stencils of reach <= 4 with affine BCs (non-uniform grids,
+//                   coefficient vectors, upwind, several operators per axis) -- merged per-row weight tables.
 int32_t star_configure(deo_plan* plan) {
     const int nd = plan->ndims;
     if (nd < 2 || nd > 3) return DEO_OK;
@@ -136,20 +272,10 @@ int32_t star_configure(deo_plan* plan) {
     const size_t es = plan->elem();
     for (int a = 0; a < nd; ++a) if (plan->padded[a]) return DEO_OK;
     if (((size_t)plan->dims[0] * es) % 16 != 0) return DEO_OK;          // TMA: row pitch must be a multiple of 16 bytes
-    if (plan->ops.size() > 3) return DEO_OK;
-    int R = 0, prev_axis = -1;
-    for (const HostOp& h : plan->ops) {
-        if (h.d.kind != DEO_OP_CENTERED || h.d.nonuniform) return DEO_OK;
-        if (h.d.axis <= prev_axis) return DEO_OK;                        // one operator per axis, in axis order (sum association)
-        prev_axis = h.d.axis;
-        R = R > h.d.stencil_length / 2 ? R : h.d.stencil_length / 2;
-    }
-    if (R < 1 || R > 4) return DEO_OK;
-    if (plan->slab_axis >= 0 && plan->slab_count < 3 * R + 3) return DEO_OK;
     const bool mid = nd == 3;
-    int kaxis[3] = {0, mid ? 1 : 2, mid ? 2 : -1};                       // plan axis -> kernel axis (x, mid, march)
+    const int kaxis[3] = {0, mid ? 1 : 2, mid ? 2 : -1};                 // plan axis -> kernel axis (x, mid, march)
+    const int paxis[3] = {0, mid ? 1 : -1, mid ? 2 : 1};                 // kernel axis -> plan axis
     auto cfg = std::make_shared<StarConfig>();
-    cfg->R = R;
     cfg->mid = mid;
     cfg->sm_count = rt().sm_count;
     const char* env_py = getenv("DEO_STAR_PY");
@@ -157,25 +283,65 @@ int32_t star_configure(deo_plan* plan) {
     if (cfg->py != 2 && cfg->py != 4) cfg->py = 2;
     const char* env_nwy = getenv("DEO_STAR_NWY");
     cfg->nwy = (env_nwy && atoi(env_nwy) == 16 && cfg->py == 2) ? 16 : 8;
-    cfg->mask = 0;
-    const bool ok = plan->dtype == DEO_F64 ? fill_params_R<double>(plan, kaxis, mid, *cfg) : fill_params_R<float>(plan, kaxis, mid, *cfg);
-    if (!ok) return DEO_OK;
-    {
-        // the edge paths read the boundary stencils' inputs from the tile: the last (possibly partial) tile along x and y
-        // must still contain them, otherwise the per-point kernel takes the plan
-        const int VEC = (int)(16 / es), HXh = ((R + VEC - 1) / VEC) * VEC, TB = 2 * R + 2;
-        const int TX = mid ? 32 * VEC : 32 * VEC * cfg->nwy * cfg->py, TY = cfg->nwy * cfg->py;
-        const long long nx = plan->dims[0], ny = mid ? plan->dims[1] : 1;
-        const int wlast = (int)((nx - 1) % TX) + 1, hlast = (int)((ny - 1) % TY) + 1;
-        const int Kx = plan->bc[0].d.K_r, Ky = mid ? plan->bc[1].d.K_r : 0;
-        if ((cfg->mask & 1) && (wlast + HXh < TB - 1 || wlast + HXh < Kx || nx < TB)) return DEO_OK;
-        if (mid && (cfg->mask & 2) && (hlast + R < TB - 1 || hlast + R < Ky || ny < TB)) return DEO_OK;
-    }
     cfg->zchunk_pref = 64;
-    cfg->zchunk_max = getenv("DEO_STAR_ZCHUNK") ? atoi(getenv("DEO_STAR_ZCHUNK")) : 64;
+    cfg->zchunk_max = getenv("DEO_STAR_ZCHUNK") ? atoi(getenv("DEO_STAR_ZCHUNK")) : 32;
     cfg->l2promo = getenv("DEO_TMA_L2PROMO") ? atoi(getenv("DEO_TMA_L2PROMO")) : 3;
+
+    // ---- CONST eligibility ----
+    bool const_ok = plan->ops.size() <= 3 && !getenv("DEO_STAR_FORCE_TABLE");
+    int R = 0, prev_axis = -1;
+    for (const HostOp& h : plan->ops) {
+        if (h.d.kind != DEO_OP_CENTERED || h.d.nonuniform) const_ok = false;
+        if (h.d.axis <= prev_axis) const_ok = false;                     // one operator per axis, in axis order (sum association)
+        prev_axis = h.d.axis;
+        R = R > h.d.stencil_length / 2 ? R : h.d.stencil_length / 2;
+    }
+    if (R < 1 || R > 4) const_ok = false;
+    if (const_ok) {
+        if (plan->slab_axis >= 0 && plan->slab_count < 3 * R + 3) return DEO_OK;
+        cfg->R = R;
+        cfg->mask = 0;
+        const bool ok = plan->dtype == DEO_F64 ? fill_params_R<double>(plan, kaxis, mid, *cfg) : fill_params_R<float>(plan, kaxis, mid, *cfg);
+        if (ok && tile_fits(plan, *cfg, mid)) {
+            for (const HostOp& h : plan->ops) if (h.d.axis == nd - 1) cfg->nedge_march = h.d.stencil_length / 2;
+            plan->star = cfg;
+            plan->kernel = "star";
+            return DEO_OK;
+        }
+    }
+    // ---- TABLE eligibility ----
+    if (getenv("DEO_STAR_NO_TABLE")) return DEO_OK;
+    AxisRows axes[3];
+    for (size_t k = 0; k < plan->ops.size(); ++k) {
+        const HostOp& h = plan->ops[k];
+        const int ka = kaxis[h.d.axis];
+        if (ka < 0 || h.d.len > (1 << 20)) return DEO_OK;
+        axes[ka].n = h.d.len;
+        axes[ka].ops.emplace_back();
+        if (plan_all_rows(plan, (int)k, axes[ka].ops.back()) != DEO_OK) return DEO_OK;
+    }
+    R = 0;
+    for (int ka = 0; ka < 3; ++ka) {
+        if (axes[ka].ops.empty()) continue;
+        const int Ra = table_radius(axes[ka]);
+        if (Ra == 0) return DEO_OK;
+        R = R > Ra ? R : Ra;
+    }
+    if (R < 1) return DEO_OK;
+    for (int ka = 0; ka < 3; ++ka) if (!axes[ka].ops.empty() && axes[ka].n < 4 * R + 4) return DEO_OK;
+    if (plan->slab_axis >= 0 && plan->slab_count < 3 * R + 3) return DEO_OK;
+    cfg->R = R;
+    cfg->mask = 0;
+    cfg->table = true;
+    cfg->py = 2;
+    cfg->nwy = 8;
+    const size_t nblobs = plan->blobs.size();
+    const bool ok = plan->dtype == DEO_F64 ? fill_params_table_R<double>(plan, axes, paxis, mid, *cfg)
+                                           : fill_params_table_R<float>(plan, axes, paxis, mid, *cfg);
+    if (!ok || !tile_fits(plan, *cfg, mid)) { plan->blobs.resize(nblobs); return DEO_OK; }
+    cfg->nedge_march = (cfg->mask & 4) ? R : 0;
     plan->star = cfg;
-    plan->kernel = "star";
+    plan->kernel = "star-table";
     return DEO_OK;
 }
 
@@ -215,8 +381,7 @@ int32_t launch_star(const deo_plan* plan, void* du, const void* u, long long z0,
         const long long row0 = ax == plan->slab_axis ? plan->slab_start : 0;
         const long long n = plan->dims[ax];
         const long long g0 = z0 + row0, g1 = z1 + row0;
-        int nlow = 0, nhigh = 0;
-        for (const HostOp& h : plan->ops) if (h.d.axis == ax) { nlow = h.d.stencil_length / 2; nhigh = nlow; }
+        const int nlow = C.nedge_march, nhigh = C.nedge_march;
         const bool low_ok = !(nlow > 0 && g0 < nlow) || (g0 == 0 && g1 > C.R);
         const bool high_ok = !(nhigh > 0 && g1 > n - nhigh) || (g1 == n && g0 <= n - 1 - C.R);
         if (!low_ok || !high_ok) return launch_generic(plan, du, u, z0, z1, s);

@@ -44,6 +44,7 @@ struct StarParams {
     T b_l[3], b_r[3];
     T azl_pad[NQ], azr_pad[NQ];  // march-axis BC stencils: a_l left-aligned, a_r right-aligned, zero padded to NQ
     T w[3][NQ];                  // interior stencil, zero padded to the template radius
+    const T* tab[3];             // TABLE variants: merged per-row interior weights [n_axis][NQ] (device), indexed by the global row
     T bw[3][2][R][TB];           // ghost-touching rows [axis][low/high][row][tap] (one-sided boundary rows and the interior
                                  // rows next to them): low rows left-aligned (tap k <-> q[k]), high rows right-aligned
                                  // (tap k <-> q[n+2-TB+k]; row i is global row n-nedge+i), zero padded
@@ -57,6 +58,8 @@ struct StarConfig {
     int py = 2;              // rows (or x segments) per thread
     int nwy = 8;             // warps per CTA (tile rows = nwy * py)
     int mask = 0;            // bit a: an operator acts along kernel axis a (x, mid, march)
+    bool table = false;      // per-row weight tables (non-uniform grids, upwind, several operators per axis)
+    int nedge_march = 0;     // rows per march-axis face that touch a ghost
     int zchunk_pref = 0;
     int zchunk_max = 0;      // experiments (DEO_STAR_ZCHUNK): upper bound on the planes per CTA along the march axis
     int l2promo = 3;         // CUtensorMapL2promotion of the tensor map (DEO_TMA_L2PROMO)
@@ -157,6 +160,8 @@ struct StarGeom {
     static constexpr int NQ = 2 * R + 1;
     static constexpr int THREADS = NWY * 32;
     static constexpr size_t SMEM = (size_t)NS * PLANE_BYTES + 2 * NS * sizeof(uint64_t);
+    static constexpr int TAB_ZMAX = 64;                            // TABLE variants: march-axis rows staged per CTA (chunk bound)
+    static constexpr size_t SMEM_TABLE = SMEM + (size_t)(TY + TAB_ZMAX) * (2 * R + 1) * sizeof(T);
     static_assert(NS >= R + 3, "ring too small");
 };
 
@@ -186,7 +191,7 @@ __device__ __forceinline__ void load_x_halo(const T* own, T (&xw)[Vec<T>::N + 2 
     }
 }
 
-template <typename T, int R, int PY, int NWY, bool MID, int MASK>
+template <typename T, int R, int PY, int NWY, bool MID, int MASK, bool TABLE>
 __global__ void __launch_bounds__(NWY * 32, ((PY <= 2 && NWY <= 8) ? 2 : 1))
 k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarParams<T, R> S,
        const T* __restrict__ u, T* __restrict__ du, int z_begin, int z_end, int zchunk) {
@@ -202,6 +207,8 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
     T* const planes = reinterpret_cast<T*>(smem_raw);      // ring of NS planes
     uint64_t* const full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * G::PLANE_BYTES);
     uint64_t* const empty = full + NS;
+    T* const sWy = reinterpret_cast<T*>(empty + NS);       // TABLE: [TY][NQ] mid-axis rows of this tile
+    T* const sWz = sWy + G::TY * NQ;                       // TABLE: [zc1 - zc0][NQ] march-axis rows of this chunk
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tx0 = blockIdx.x * G::TX;
@@ -231,6 +238,18 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         for (int k0 = 0; k0 < NS && k0 < n_planes; ++k0) issue_plane(k0);
     }
+    if constexpr (TABLE) {
+        if constexpr (has_y) {
+            for (int i = threadIdx.x; i < G::TY * NQ; i += G::THREADS) {
+                const int gyr = min(ty0 + i / NQ, S.ny - 1);
+                sWy[i] = __ldg(S.tab[1] + (long long)gyr * NQ + i % NQ);
+            }
+        }
+        if constexpr (has_z) {
+            for (int i = threadIdx.x; i < (zc1 - zc0) * NQ; i += G::THREADS)
+                sWz[i] = __ldg(S.tab[2] + (long long)(zc0 + S.row0_z + i / NQ) * NQ + i % NQ);
+        }
+    }
     __syncthreads();
 
     const int wy = warp;
@@ -253,6 +272,16 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
         }
         live[j] = gx[j] < nx && gy[j] < ny;
         optr[j] = du + (long long)gx[j] + (long long)gy[j] * S.osy + (long long)zc0 * S.osz;
+    }
+    // TABLE: the x-axis weights of this thread's own points stay in registers for the whole chunk
+    T wx[(TABLE && has_x) ? (MID ? 1 : PY) : 1][(TABLE && has_x) ? VEC : 1][(TABLE && has_x) ? NQ : 1];
+    if constexpr (TABLE && has_x) {
+#pragma unroll
+        for (int j = 0; j < (MID ? 1 : PY); ++j)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+#pragma unroll
+                for (int t = 0; t < NQ; ++t) wx[j][v][t] = __ldg(S.tab[0] + (long long)min(gx[j] + v, nx - 1) * NQ + t);
     }
     // CTA-uniform face flags: only tiles on a face execute any edge code
     const bool xlo_tile = has_x && tx0 == 0, xhi_tile = has_x && tx0 + G::TX >= nx;
@@ -335,7 +364,10 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
                     for (int v = 0; v < VEC; ++v) {
                         T a = T(0);
 #pragma unroll
-                        for (int t = 0; t < NQ; ++t) a = fma_t(S.w[0][t], xw[v + t], a);
+                        for (int t = 0; t < NQ; ++t) {
+                            if constexpr (TABLE) a = fma_t(wx[MID ? 0 : j][v][t], xw[v + t], a);
+                            else a = fma_t(S.w[0][t], xw[v + t], a);
+                        }
                         tot[j][v] = a;
                     }
                 }
@@ -430,8 +462,9 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
                     for (int j = 0; j < PY; ++j) {
                         const int t = r - j;
                         if (t >= 0 && t < NQ) {
+                            const T wyt = TABLE ? sWy[(wy * PY + j) * NQ + t] : S.w[1][t];
 #pragma unroll
-                            for (int v = 0; v < VEC; ++v) acc[j][v] = fma_t(S.w[1][t], row[v], acc[j][v]);
+                            for (int v = 0; v < VEC; ++v) acc[j][v] = fma_t(wyt, row[v], acc[j][v]);
                         }
                     }
                 }
@@ -489,13 +522,16 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
             if constexpr (has_z) {
                 const bool z_low_edge = EDGE && gz < ez, z_high_edge = EDGE && gz >= S.nglob_z - ez;
                 if (!(z_low_edge || z_high_edge)) {
+                    T wz[NQ];
+#pragma unroll
+                    for (int t = 0; t < NQ; ++t) wz[t] = TABLE ? sWz[(z - zc0) * NQ + t] : S.w[2][t];
 #pragma unroll
                     for (int j = 0; j < PY; ++j) {
 #pragma unroll
                         for (int v = 0; v < VEC; ++v) {
                             T s = T(0);
 #pragma unroll
-                            for (int t = 0; t < NQ; ++t) s = fma_t(S.w[2][t], zq[j][v][P(t)], s);
+                            for (int t = 0; t < NQ; ++t) s = fma_t(wz[t], zq[j][v][P(t)], s);
                             tot[j][v] = (has_x || has_y) ? tot[j][v] + s : s;
                         }
                     }
@@ -626,48 +662,48 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
     while (z < zc1) step(std::true_type{}, std::true_type{}, Shift{});
 }
 
-template <typename T, int R, int PY, int NWY, bool MID, int MASK>
+template <typename T, int R, int PY, int NWY, bool MID, int MASK, bool TABLE>
 int32_t launch_variant(const StarConfig& C, const void* u, void* du, long long z0, long long z1, cudaStream_t s) {
     using G = StarGeom<T, R, PY, NWY, MID>;
     const StarParams<T, R>& S = *reinterpret_cast<const StarParams<T, R>*>(C.params.data());
-    static bool attr_set = false, attr_set2 = false;
-    auto kern = k_star<T, R, PY, NWY, MID, MASK>;
+    constexpr size_t SMEM = TABLE ? G::SMEM_TABLE : G::SMEM;
+    static bool attr_set = false;
+    auto kern = k_star<T, R, PY, NWY, MID, MASK, TABLE>;
     if (!attr_set) {
-        DEO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
+        DEO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
         attr_set = true;
     }
     // the tensor map addresses the buffer it was encoded for; re-encode when the caller passes another one
     CUtensorMap map = C.tmap;
     const long long len = z1 - z0;
     const long long tiles = (long long)((S.nx + G::TX - 1) / G::TX) * (MID ? (S.ny + G::TY - 1) / G::TY : 1);
-    // chunking of the march axis: fill the SMs, keep the 2R priming planes per chunk cheap, never cut a face's one-sided rows
-    long long zc = C.zchunk_pref;
+    // Chunking of the march axis.  Short chunks keep the CTAs of a wave in step, so that the halo rows/columns a tile
+    // shares with its neighbours are still in L2 when the neighbour asks for them (long chunks let face tiles, which
+    // do extra work, drift away: measured on B200, DRAM reads grow from 1.1x to 1.6x the field).  Among the chunk
+    // lengths <= zchunk_max pick the one with the shortest makespan in plane-steps (each CTA also primes 2R planes);
+    // never cut a face's one-sided rows.
+    long long zmax = C.zchunk_max > 0 ? C.zchunk_max : len;
+    if (TABLE && zmax > G::TAB_ZMAX) zmax = G::TAB_ZMAX;
+    if (zmax < 4 * R + 4) zmax = 4 * R + 4;
+    long long zc = len;
     {
         double best = 1e30;
-        long long best_zc = len;
-        for (long long nch = 1; nch <= len; ++nch) {
-            long long c = (len + nch - 1) / nch;
+        const long long slots = (long long)C.sm_count * G::CTAS_PER_SM;
+        for (long long nch = (len + zmax - 1) / zmax; nch <= len; ++nch) {
+            const long long c = (len + nch - 1) / nch;
             if (c < 4 * R + 4 && nch > 1) break;
-            if (C.zchunk_max > 0 && c > C.zchunk_max && c > 4 * R + 4) continue;
             const long long nchunks = (len + c - 1) / c;
             const long long last = len - (nchunks - 1) * c;
             if (nchunks > 1 && last < R + 1) continue;
-            const long long ctas = tiles * nchunks;
-            const long long slots = (long long)C.sm_count * G::CTAS_PER_SM;
-            const long long waves = (ctas + slots - 1) / slots;
-            const double cost = (double)waves * (double)(c + 2 * R);   // makespan in plane-steps (each CTA also primes 2R planes)
-            if (cost < best - 1e-12) { best = cost; best_zc = c; }
-            if (ctas > 64LL * C.sm_count && C.zchunk_max == 0) break;
+            const long long waves = (tiles * nchunks + slots - 1) / slots;
+            const double cost = (double)waves * (double)(c + 2 * R);
+            if (cost < best - 1e-12) { best = cost; zc = c; }
+            if (c * 2 < zmax) break;                       // do not go below half the bound
         }
-        zc = best_zc;
+        if (TABLE && zc > G::TAB_ZMAX) { set_error("star kernel: march-axis range too short to chunk"); return DEO_ERR_UNSUPPORTED; }
     }
     dim3 grid((unsigned)((S.nx + G::TX - 1) / G::TX), (unsigned)(MID ? (S.ny + G::TY - 1) / G::TY : 1), (unsigned)((len + zc - 1) / zc));
-    static const size_t extra_smem = getenv("DEO_STAR_EXTRA_SMEM") ? (size_t)atoll(getenv("DEO_STAR_EXTRA_SMEM")) : 0;   // occupancy experiments
-    if (extra_smem && !attr_set2) {
-        DEO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(G::SMEM + extra_smem)));
-        attr_set2 = true;
-    }
-    kern<<<grid, G::THREADS, G::SMEM + extra_smem, s>>>(map, S, (const T*)u, (T*)du, (int)z0, (int)z1, (int)zc);
+    kern<<<grid, G::THREADS, SMEM, s>>>(map, S, (const T*)u, (T*)du, (int)z0, (int)z1, (int)zc);
     DEO_CUDA(cudaGetLastError());
     return DEO_OK;
 }
@@ -677,36 +713,38 @@ int32_t launch_variant(const StarConfig& C, const void* u, void* du, long long z
 template <typename T, int R>
 int32_t star_launch_R(const StarConfig& C, const void* u, void* du, long long z0, long long z1, cudaStream_t s);
 
-template <typename T, int R, int PY, int NWY, bool MID>
+template <typename T, int R, int PY, int NWY, bool MID, bool TABLE>
 int32_t star_launch_mask(const StarConfig& C, const void* u, void* du, long long z0, long long z1, cudaStream_t s) {
     switch (C.mask) {
-        case 1: return launch_variant<T, R, PY, NWY, MID, 1>(C, u, du, z0, z1, s);
-        case 4: return launch_variant<T, R, PY, NWY, MID, 4>(C, u, du, z0, z1, s);
-        case 5: return launch_variant<T, R, PY, NWY, MID, 5>(C, u, du, z0, z1, s);
+        case 1: return launch_variant<T, R, PY, NWY, MID, 1, TABLE>(C, u, du, z0, z1, s);
+        case 4: return launch_variant<T, R, PY, NWY, MID, 4, TABLE>(C, u, du, z0, z1, s);
+        case 5: return launch_variant<T, R, PY, NWY, MID, 5, TABLE>(C, u, du, z0, z1, s);
     }
     if constexpr (MID) {
         switch (C.mask) {
-            case 2: return launch_variant<T, R, PY, NWY, MID, 2>(C, u, du, z0, z1, s);
-            case 3: return launch_variant<T, R, PY, NWY, MID, 3>(C, u, du, z0, z1, s);
-            case 6: return launch_variant<T, R, PY, NWY, MID, 6>(C, u, du, z0, z1, s);
-            case 7: return launch_variant<T, R, PY, NWY, MID, 7>(C, u, du, z0, z1, s);
+            case 2: return launch_variant<T, R, PY, NWY, MID, 2, TABLE>(C, u, du, z0, z1, s);
+            case 3: return launch_variant<T, R, PY, NWY, MID, 3, TABLE>(C, u, du, z0, z1, s);
+            case 6: return launch_variant<T, R, PY, NWY, MID, 6, TABLE>(C, u, du, z0, z1, s);
+            case 7: return launch_variant<T, R, PY, NWY, MID, 7, TABLE>(C, u, du, z0, z1, s);
         }
     }
     set_error("star kernel: unsupported operator mask %d", C.mask);
     return DEO_ERR_UNSUPPORTED;
 }
 
-template <typename T, int R, int PY, int NWY>
+template <typename T, int R, int PY, int NWY, bool TABLE>
 int32_t star_launch_mid(const StarConfig& C, const void* u, void* du, long long z0, long long z1, cudaStream_t s) {
-    return C.mid ? star_launch_mask<T, R, PY, NWY, true>(C, u, du, z0, z1, s) : star_launch_mask<T, R, PY, NWY, false>(C, u, du, z0, z1, s);
+    return C.mid ? star_launch_mask<T, R, PY, NWY, true, TABLE>(C, u, du, z0, z1, s)
+                 : star_launch_mask<T, R, PY, NWY, false, TABLE>(C, u, du, z0, z1, s);
 }
 
 #define DEO_STAR_INSTANTIATE(R_)                                                                                              \
     template <typename T, int R>                                                                                              \
     int32_t star_launch_R(const StarConfig& C, const void* u, void* du, long long z0, long long z1, cudaStream_t s) {        \
-        if (C.py == 2 && C.nwy == 16) return star_launch_mid<T, R, 2, 16>(C, u, du, z0, z1, s);                              \
-        if (C.py == 2) return star_launch_mid<T, R, 2, 8>(C, u, du, z0, z1, s);                                               \
-        return star_launch_mid<T, R, 4, 8>(C, u, du, z0, z1, s);                                                              \
+        if (C.table) return star_launch_mid<T, R, 2, 8, true>(C, u, du, z0, z1, s);                                           \
+        if (C.py == 2 && C.nwy == 16) return star_launch_mid<T, R, 2, 16, false>(C, u, du, z0, z1, s);                       \
+        if (C.py == 2) return star_launch_mid<T, R, 2, 8, false>(C, u, du, z0, z1, s);                                        \
+        return star_launch_mid<T, R, 4, 8, false>(C, u, du, z0, z1, s);                                                       \
     }                                                                                                                          \
     template int32_t star_launch_R<double, R_>(const StarConfig&, const void*, void*, long long, long long, cudaStream_t);    \
     template int32_t star_launch_R<float, R_>(const StarConfig&, const void*, void*, long long, long long, cudaStream_t);

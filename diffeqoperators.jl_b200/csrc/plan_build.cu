@@ -349,7 +349,45 @@ int32_t build_typed(deo_plan* plan) {
     return DEO_OK;
 }
 
+// Every output row of operator H as "row r = sum_k w[k] * q[start + k]" (0-based rows; w = c*w as the reference forms it),
+// by replaying left / interior / right exactly like build_op.  Used by the tiled kernel's merged-table builder.
+template <typename T>
+int32_t all_rows_typed(const HostOp& H, bool bpv, std::vector<HostRow>& out) {
+    OpView<T> A(H);
+    const bool upwind = H.d.kind == DEO_OP_UPWIND;
+    const bool nonuni = H.d.nonuniform != 0;
+    const int n = A.n;
+    const int int_first = A.bpc + 1;
+    const int int_last = upwind ? n - A.bpc - A.off : n - A.bpc;
+    RowSink<T> S;
+    S.n = n;
+    if (!upwind) centered_left(A, S); else if (!nonuni) upwind_u_left(A, S); else upwind_n_left(A, S);
+    for (int i = int_first; i <= int_last; ++i) {
+        if (!upwind) centered_interior_row(A, S, i, bpv);
+        else if (!nonuni) upwind_u_interior_row(A, S, i);
+        else upwind_n_interior_row(A, S, i);
+    }
+    if (!upwind) centered_right(A, S, bpv); else if (!nonuni) upwind_u_right(A, S); else upwind_n_right(A, S);
+    DEO_REQUIRE(S.ok, "op on axis %d (len %d): %s", H.d.axis, n, S.why.c_str());
+    out.assign((size_t)n, HostRow{});
+    for (int i = 1; i <= n; ++i) {
+        auto it = S.rows.find(i);
+        DEO_REQUIRE(it != S.rows.end(), "op on axis %d (len %d): row %d is written by no convolution", H.d.axis, n, i);
+        HostRow& r = out[(size_t)i - 1];
+        r.start = it->second.start;
+        r.ntaps = it->second.ntaps;
+        for (int k = 0; k < kMaxBTaps; ++k) r.w[k] = k < r.ntaps ? (double)it->second.w[k] : 0.0;
+    }
+    return DEO_OK;
+}
+
 }  // namespace
+
+int32_t plan_all_rows(const deo_plan* plan, int k, std::vector<HostRow>& out) {
+    const HostOp& H = plan->ops[(size_t)k];
+    const bool bpv = plan->ndims == 1 && plan->bc[H.d.axis].d.kind != DEO_BC_NONE;
+    return plan->dtype == DEO_F64 ? all_rows_typed<double>(H, bpv, out) : all_rows_typed<float>(H, bpv, out);
+}
 
 int32_t build_device_plan(deo_plan* plan) {
     return plan->dtype == DEO_F64 ? build_typed<double>(plan) : build_typed<float>(plan);

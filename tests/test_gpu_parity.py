@@ -287,6 +287,9 @@ def test_config4_nonuniform_centered_plus_upwind(D, O, dtype, generic):
             A = A + p[0]
         got = D.mul_alloc(A * Q, u, flags=_flags(D, generic))
         assert_close(got, O.apply_sum([p[1] for p in pairs], u, bcs), dtype, f"C4 {name}")
+        # the tiled kernel takes non-uniform / upwind / multi-operator sums through its merged per-row tables
+        kern = D.build_plans(A * Q, shape, shape, dtype, flags=_flags(D, generic))[0][0].info[0]
+        assert kern == ("generic" if generic else "star-table"), kern
 
 
 def test_nd_single_directional_bc(D, O):
