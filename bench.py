@@ -36,8 +36,18 @@ WORKLOADS = {
     "C3f32": ((512, 512, 512), 6, np.float32, "C3: 3-D Laplacian (2,6) + Neumann MultiDimBC, 512^3 Float32"),
     "C2": ((8192, 8192), 4, np.float64, "C2: 2-D Laplacian Dxx+Dyy (2,4) + RobinBC, 8192^2 Float64"),
     "C1": ((10 ** 6,), 2, np.float64, "C1: 1-D heat-equation Laplacian CenteredDifference(2,2)*Dirichlet0BC, N=1e6 Float64"),
+    "C4": ((512, 512, 512), 4, np.float64, "C4: non-uniform 512^3 Float64, sum over axes of CenteredDifference(2,4) + CenteredDifference(1,4) + "
+           "UpwindDifference(1,2) with a mixed-sign coefficient vector, RobinBC from the same spacings (9 operators, one pass)"),
 }
 ROBIN_L, ROBIN_R = (1.0, 0.5, 0.25), (1.0, -0.5, 0.75)
+
+
+def c4_inputs(shape, dtype):
+    """Spacing vectors and coefficient vectors of BASELINE config 4."""
+    hs = [1.0 / (s + 1) for s in shape]
+    dxs = [(h * (1 + 0.3 * np.sin(2 * np.pi * np.arange(1, s + 2) / (s + 1)))).astype(dtype) for s, h in zip(shape, hs)]
+    cs = [np.sin(6 * np.pi * np.arange(1, s + 1) / s).astype(dtype) for s in shape]
+    return dxs, cs
 
 
 def build_operator(D, name, shape, dtype):
@@ -45,6 +55,15 @@ def build_operator(D, name, shape, dtype):
     _, a, _, _ = WORKLOADS[name]
     nd = len(shape)
     h = tuple(1.0 / (s + 1) for s in shape)
+    if name == "C4":
+        dxs, cs = c4_inputs(shape, dtype)
+        ops = [D.CenteredDifference[ax](2, 4, dxs[ax - 1], shape[ax - 1], dtype=dtype) for ax in range(1, nd + 1)] + \
+              [D.CenteredDifference[ax](1, 4, dxs[ax - 1], shape[ax - 1], dtype=dtype) for ax in range(1, nd + 1)] + \
+              [D.UpwindDifference[ax](1, 2, dxs[ax - 1], shape[ax - 1], cs[ax - 1], dtype=dtype) for ax in range(1, nd + 1)]
+        A = ops[0]
+        for o in ops[1:]:
+            A = A + o
+        return A * D.compose(*D.RobinBC(ROBIN_L, ROBIN_R, dxs, 1, shape, dtype=dtype))
     if nd == 1:
         return D.CenteredDifference(2, a, h[0], shape[0], dtype=dtype) * D.Dirichlet0BC(dtype)
     A = D.CenteredDifference[1](2, a, h[0], shape[0], dtype=dtype)
@@ -61,6 +80,12 @@ def build_oracle(O, name, shape, dtype):
     _, a, _, _ = WORKLOADS[name]
     nd = len(shape)
     h = tuple(1.0 / (s + 1) for s in shape)
+    if name == "C4":
+        dxs, cs = c4_inputs(shape, dtype)
+        ops = [O.CenteredDifference(2, 4, dxs[ax], shape[ax], axis=ax + 1, dtype=dtype) for ax in range(nd)] + \
+              [O.CenteredDifference(1, 4, dxs[ax], shape[ax], axis=ax + 1, dtype=dtype) for ax in range(nd)] + \
+              [O.UpwindDifference(1, 2, dxs[ax], shape[ax], cs[ax], axis=ax + 1, dtype=dtype) for ax in range(nd)]
+        return ops, {ax + 1: O.RobinBC(ROBIN_L, ROBIN_R, dxs[ax], 1, dtype) for ax in range(nd)}
     ops = [O.CenteredDifference(2, a, h[ax], shape[ax], axis=ax + 1, dtype=dtype) for ax in range(nd)]
     if nd == 1:
         bcs = {1: O.Dirichlet0BC(dtype)}
@@ -104,55 +129,96 @@ def time_oracle(name, dtype, steps, warmup, nthreads):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).  NVML is polled from a
+    thread every few milliseconds (the timed region is tens of milliseconds, too short for `nvidia-smi -lms`); if NVML
+    is not importable the nvidia-smi loop is used instead."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
         self.device = device
-        self.lines = []
+        self.samples = []          # (sm_mhz, max_mhz, reasons bitmask or set)
         self.proc = None
+        self.stop = threading.Event()
+        self.thread = None
+        self.nvml = None
+
+    def _index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.device])
+            except Exception:
+                return self.device
+        return self.device
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._index())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return self
+        except Exception:
+            self.nvml = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
+                                          "-i", str(self._index())], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read_smi, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _poll_nvml(self):
+        n = self.nvml
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop.is_set():
+            try:
+                self.samples.append((float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)), self.max_mhz, int(get_reasons(self.handle))))
+            except Exception:
+                pass
+            time.sleep(0.003)
+
+    def _read_smi(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.proc.stdout:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                self.samples.append((float(f[1]), float(f[2]), {nm for nm, val in zip(names, f[5:9]) if val.lower().startswith("active")}))
+            except ValueError:
+                continue
 
     def __exit__(self, *exc):
+        self.stop.set()
         if self.proc is not None:
-            time.sleep(0.15)
+            time.sleep(0.05)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        if not sm:
+        if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        sm = [s[0] for s in self.samples]
+        reasons = set()
+        for s in self.samples:
+            if isinstance(s[2], set):
+                reasons |= s[2]
+            else:
+                bits = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+                reasons |= {nm for b, nm in bits.items() if s[2] & b}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(s[1] for s in self.samples)), "reasons": sorted(reasons),
+                "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def measured_peak():

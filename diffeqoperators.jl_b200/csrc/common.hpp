@@ -41,6 +41,8 @@ struct Runtime {
     int device = -1;
     cudaStream_t stream = nullptr;        // compute stream of the library
     cudaStream_t comm_stream = nullptr;   // halo-exchange stream
+    cudaStream_t h2d_stream = nullptr;    // host-buffer path: upload / download streams of the chunk pipeline
+    cudaStream_t d2h_stream = nullptr;
     int sm_count = 0;
     bool ready = false;
 };
@@ -162,7 +164,13 @@ struct deo_plan {
     std::vector<unsigned char> devplan;     // DevPlan<T> bytes
     std::string kernel = "generic";
     int launches_per_apply = 1;
-    std::shared_ptr<void> star;             // StarConfig when the fast path is eligible
+    std::shared_ptr<void> star;             // StarConfig when the tiled 2-D/3-D kernel is eligible
+    std::shared_ptr<void> line;             // LineConfig when the 1-D kernel is eligible
+
+    // host-buffer path (deo_plan_apply_host): device staging buffers kept across calls, pipeline events
+    deo_buffer* host_u = nullptr;
+    deo_buffer* host_du = nullptr;
+    std::vector<cudaEvent_t> host_ev;
 
     // graph cache for apply_n
     cudaGraphExec_t graph_exec = nullptr;
@@ -183,12 +191,22 @@ namespace deo {
 // plan_build.cu
 int32_t build_device_plan(deo_plan* plan);
 struct HostRow { int start = 0, ntaps = 0; double w[kMaxBTaps]; };   // row r = sum_k w[k] * q[start + k]
-int32_t plan_all_rows(const deo_plan* plan, int op_index, std::vector<HostRow>& rows);
+struct RowGenerator {                      // lazily enumerates the rows of one operator of a plan
+    int n = 0;
+    bool interior_uniform = false;         // uniform grid and constant coefficient: every interior row has the same weights
+    virtual ~RowGenerator() {}
+    virtual bool ok() const = 0;
+    virtual bool row(int r0, HostRow& out) = 0;   // 0-based row
+};
+std::unique_ptr<RowGenerator> make_row_generator(const deo_plan* plan, int op_index);
 // kernel_generic.cu : computes local output planes [z0, z1) of the last axis (whole array when ndims<3 uses z in [0,1))
 int32_t launch_generic(const deo_plan* plan, void* du, const void* u, long long z0, long long z1, cudaStream_t s);
 // kernel_star.cu
 int32_t star_configure(deo_plan* plan);
-int32_t launch_star(const deo_plan* plan, void* du, const void* u, long long z0, long long z1, cudaStream_t s);
+int32_t launch_star(const deo_plan* plan, void* du, const void* u, long long z0, long long z1, cudaStream_t s, bool explicit_range = false);
+// kernel_line.cu
+int32_t line_configure(deo_plan* plan);
+int32_t launch_line(const deo_plan* plan, void* du, const void* u, cudaStream_t s);
 // plan.cu
 int32_t launch_plan(const deo_plan* plan, void* du, const void* u, long long z0, long long z1, cudaStream_t s);
 }  // namespace deo

@@ -318,7 +318,11 @@ int32_t star_configure(deo_plan* plan) {
         if (ka < 0 || h.d.len > (1 << 20)) return DEO_OK;
         axes[ka].n = h.d.len;
         axes[ka].ops.emplace_back();
-        if (plan_all_rows(plan, (int)k, axes[ka].ops.back()) != DEO_OK) return DEO_OK;
+        auto gen = make_row_generator(plan, (int)k);
+        if (!gen->ok()) return DEO_OK;
+        std::vector<HostRow>& rows = axes[ka].ops.back();
+        rows.resize((size_t)h.d.len);
+        for (int r = 0; r < h.d.len; ++r) if (!gen->row(r, rows[(size_t)r])) return DEO_OK;
     }
     R = 0;
     for (int ka = 0; ka < 3; ++ka) {
@@ -345,7 +349,7 @@ int32_t star_configure(deo_plan* plan) {
     return DEO_OK;
 }
 
-int32_t launch_star(const deo_plan* plan, void* du, const void* u, long long z0, long long z1, cudaStream_t s) {
+int32_t launch_star(const deo_plan* plan, void* du, const void* u, long long z0, long long z1, cudaStream_t s, bool explicit_range) {
     StarConfig& C = *static_cast<StarConfig*>(plan->star.get());
     PFN_encodeTiled enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return DEO_ERR_CUDA; }
@@ -372,7 +376,7 @@ int32_t launch_star(const deo_plan* plan, void* du, const void* u, long long z0,
                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return DEO_ERR_CUDA; }
-    if (!mid) { z0 = 0; z1 = plan->local_dim(plan->ndims - 1); }   // 2-D arrays stream along their last axis
+    if (!mid && !explicit_range) { z0 = 0; z1 = plan->local_dim(plan->ndims - 1); }   // 2-D arrays stream along their last axis
     // The one-sided rows of the march axis take their term from the register queue at the steps whose centre is
     // global plane R (low face) / n-1-R (high face); a launch range that contains such rows but not that step
     // (never produced by this library's own callers) runs on the per-point kernel instead.
@@ -384,7 +388,10 @@ int32_t launch_star(const deo_plan* plan, void* du, const void* u, long long z0,
         const int nlow = C.nedge_march, nhigh = C.nedge_march;
         const bool low_ok = !(nlow > 0 && g0 < nlow) || (g0 == 0 && g1 > C.R);
         const bool high_ok = !(nhigh > 0 && g1 > n - nhigh) || (g1 == n && g0 <= n - 1 - C.R);
-        if (!low_ok || !high_ok) return launch_generic(plan, du, u, z0, z1, s);
+        if (!low_ok || !high_ok) {
+            if (!mid) { set_error("star kernel: 2-D row range [%lld, %lld) cuts a face's one-sided rows", z0, z1); return DEO_ERR_UNSUPPORTED; }
+            return launch_generic(plan, du, u, z0, z1, s);
+        }
     }
     return plan->dtype == DEO_F64 ? dispatch_T<double>(C, u, du, z0, z1, s) : dispatch_T<float>(C, u, du, z0, z1, s);
 }

@@ -1,5 +1,7 @@
 // Plan objects of libdeo_b200: validation and deep copy of the caller's operand bundles, kernel
 // dispatch, CUDA-graph replay for repeated applications, the host-buffer path.
+#include <cstdlib>
+
 #include "common.hpp"
 
 using namespace deo;
@@ -101,8 +103,11 @@ int32_t finalize_plan(deo_plan* plan) {
     plan->kernel = "generic";
     plan->launches_per_apply = 1;
     plan->star.reset();
+    plan->line.reset();
     if (!(plan->flags & DEO_FLAG_FORCE_GENERIC)) {
-        rc = star_configure(plan);   // sets plan->kernel = "star" when eligible
+        rc = star_configure(plan);   // sets plan->kernel = "star" / "star-table" when eligible
+        if (rc) return rc;
+        rc = line_configure(plan);   // 1-D plans: "line" / "line-table"
         if (rc) return rc;
     }
     if (plan->graph_exec) { cudaGraphExecDestroy(plan->graph_exec); plan->graph_exec = nullptr; }
@@ -112,6 +117,7 @@ int32_t finalize_plan(deo_plan* plan) {
 int32_t launch_plan(const deo_plan* plan, void* du, const void* u, long long z0, long long z1, cudaStream_t s) {
     if (z1 <= z0) return DEO_OK;
     if (plan->star) return launch_star(plan, du, u, z0, z1, s);
+    if (plan->line) return launch_line(plan, du, u, s);
     return launch_generic(plan, du, u, z0, z1, s);
 }
 
@@ -168,6 +174,9 @@ int32_t deo_plan_destroy(deo_plan* plan) {
     if (!plan) return DEO_OK;
     if (rt().ready) { cudaStreamSynchronize(rt().stream); cudaStreamSynchronize(rt().comm_stream); }
     if (plan->graph_exec) cudaGraphExecDestroy(plan->graph_exec);
+    if (plan->host_u) deo_buffer_free(plan->host_u);
+    if (plan->host_du) deo_buffer_free(plan->host_du);
+    for (cudaEvent_t e : plan->host_ev) cudaEventDestroy(e);
     delete plan;
     return DEO_OK;
 }
@@ -200,27 +209,76 @@ int32_t deo_plan_apply_n(deo_plan* plan, deo_buffer* du, const deo_buffer* u, in
     return DEO_OK;
 }
 
+// Host-buffer form of mul!.  The field is cut into chunks of planes along the last axis and pushed through a
+// three-stage pipeline on three streams -- upload chunk k+1 | fused kernel on chunk k | download chunk k-1 -- so the two
+// PCIe directions and the kernel overlap; the kernel of chunk k needs the first `reach` planes of chunk k+1, so it
+// waits for that upload.  The device staging buffers are allocated on the first call and kept by the plan.
 int32_t deo_plan_apply_host(deo_plan* plan, void* du_host, const void* u_host) {
     DEO_REQUIRE(plan && du_host && u_host, "deo_plan_apply_host: null argument");
+    DEO_REQUIRE(plan->dist == nullptr && plan->nranks == 1, "deo_plan_apply_host: slab plans go through deo_dist_plan_apply");
     const size_t in_b = plan->in_elems() * plan->elem(), out_b = plan->out_elems() * plan->elem();
-    deo_buffer *u = nullptr, *du = nullptr;
-    int32_t rc = deo_buffer_create(in_b, &u);
-    if (rc) return rc;
-    rc = deo_buffer_create(out_b, &du);
-    if (rc) { deo_buffer_free(u); return rc; }
-    cudaStream_t s = rt().stream;
-    cudaError_t e = cudaMemcpyAsync(u->ptr, u_host, in_b, cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess && plan->accumulate) e = cudaMemcpyAsync(du->ptr, du_host, out_b, cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess) {
+    int32_t rc = DEO_OK;
+    if (!plan->host_u) { rc = deo_buffer_create(in_b, &plan->host_u); if (rc) return rc; }
+    if (!plan->host_du) { rc = deo_buffer_create(out_b, &plan->host_du); if (rc) return rc; }
+    deo_buffer *u = plan->host_u, *du = plan->host_du;
+    Runtime& R = rt();
+    cudaStream_t s = R.stream;
+    const int last = plan->ndims - 1;
+    const long long nlast = plan->local_dim(last);
+    const size_t in_plane = in_b / (size_t)plan->in_dim(last), out_plane = out_b / (size_t)nlast;
+    // planes the operators along the last axis reach across (one-sided boundary rows included), and chunk length
+    int reach = 0;
+    for (const HostOp& h : plan->ops)
+        if (h.d.axis == last) reach = reach > h.d.boundary_stencil_length ? reach : h.d.boundary_stencil_length;
+    const size_t chunk_bytes = getenv("DEO_HOST_CHUNK_BYTES") ? (size_t)atoll(getenv("DEO_HOST_CHUNK_BYTES")) : ((size_t)96 << 20);
+    long long chunk = (long long)(chunk_bytes / (out_plane ? out_plane : 1));
+    if (chunk < 2 * reach + 8) chunk = 2 * reach + 8;
+    const bool rangeable = plan->ndims == 3 || (plan->ndims == 2 && plan->star);   // kernels that take a range of the last axis
+    const long long nchunks = rangeable ? (nlast + chunk - 1) / chunk : 1;
+    const bool pipelined = nchunks >= 3 && !plan->padded[last] && plan->bc[last].d.kind != DEO_BC_PERIODIC &&
+                           nlast - (nchunks - 1) * chunk >= 2 * reach + 2;
+    if (!pipelined) {
+        DEO_CUDA(cudaMemcpyAsync(u->ptr, u_host, in_b, cudaMemcpyHostToDevice, s));
+        if (plan->accumulate) DEO_CUDA(cudaMemcpyAsync(du->ptr, du_host, out_b, cudaMemcpyHostToDevice, s));
         rc = launch_plan(plan, du->ptr, u->ptr, 0, last_extent(plan), s);
         g_launches += plan->launches_per_apply;
-        if (rc == DEO_OK) e = cudaMemcpyAsync(du_host, du->ptr, out_b, cudaMemcpyDeviceToHost, s);
+        if (rc) return rc;
+        DEO_CUDA(cudaMemcpyAsync(du_host, du->ptr, out_b, cudaMemcpyDeviceToHost, s));
+        DEO_CUDA(cudaStreamSynchronize(s));
+        return DEO_OK;
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    deo_buffer_free(u);
-    deo_buffer_free(du);
-    if (e != cudaSuccess) return cuda_fail(e, "deo_plan_apply_host", __FILE__, __LINE__);
-    return rc;
+    while ((long long)plan->host_ev.size() < 2 * nchunks) {
+        cudaEvent_t e;
+        DEO_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        plan->host_ev.push_back(e);
+    }
+    DEO_CUDA(cudaStreamSynchronize(s));
+    // stage 1: uploads, in order, on the upload stream
+    for (long long k = 0; k < nchunks; ++k) {
+        const long long z0 = k * chunk, z1 = (k + 1) * chunk < nlast ? (k + 1) * chunk : nlast;
+        DEO_CUDA(cudaMemcpyAsync((char*)u->ptr + (size_t)z0 * in_plane, (const char*)u_host + (size_t)z0 * in_plane, (size_t)(z1 - z0) * in_plane,
+                                 cudaMemcpyHostToDevice, R.h2d_stream));
+        if (plan->accumulate)
+            DEO_CUDA(cudaMemcpyAsync((char*)du->ptr + (size_t)z0 * out_plane, (const char*)du_host + (size_t)z0 * out_plane,
+                                     (size_t)(z1 - z0) * out_plane, cudaMemcpyHostToDevice, R.h2d_stream));
+        DEO_CUDA(cudaEventRecord(plan->host_ev[(size_t)k], R.h2d_stream));
+    }
+    // stages 2 and 3: kernel on chunk k once chunk k+1 has landed, download behind it
+    for (long long k = 0; k < nchunks; ++k) {
+        const long long z0 = k * chunk, z1 = (k + 1) * chunk < nlast ? (k + 1) * chunk : nlast;
+        DEO_CUDA(cudaStreamWaitEvent(s, plan->host_ev[(size_t)(k + 1 < nchunks ? k + 1 : k)], 0));
+        if (plan->ndims == 3) rc = launch_plan(plan, du->ptr, u->ptr, z0, z1, s);
+        else rc = launch_star(plan, du->ptr, u->ptr, z0, z1, s, true);     // 2-D: a range of rows of the last axis
+        if (rc) return rc;
+        g_launches += plan->launches_per_apply;
+        DEO_CUDA(cudaEventRecord(plan->host_ev[(size_t)(nchunks + k)], s));
+        DEO_CUDA(cudaStreamWaitEvent(R.d2h_stream, plan->host_ev[(size_t)(nchunks + k)], 0));
+        DEO_CUDA(cudaMemcpyAsync((char*)du_host + (size_t)z0 * out_plane, (const char*)du->ptr + (size_t)z0 * out_plane, (size_t)(z1 - z0) * out_plane,
+                                 cudaMemcpyDeviceToHost, R.d2h_stream));
+    }
+    DEO_CUDA(cudaStreamSynchronize(R.d2h_stream));
+    DEO_CUDA(cudaStreamSynchronize(s));
+    return DEO_OK;
 }
 
 int32_t deo_plan_info(const deo_plan* plan, char* kernel_name, size_t len, int32_t* launches_per_apply) {

@@ -350,43 +350,59 @@ int32_t build_typed(deo_plan* plan) {
 }
 
 // Every output row of operator H as "row r = sum_k w[k] * q[start + k]" (0-based rows; w = c*w as the reference forms it),
-// by replaying left / interior / right exactly like build_op.  Used by the tiled kernel's merged-table builder.
+// produced lazily with the same left / interior / right logic as build_op.  Used by the merged-table builders of the
+// tiled kernels (kernel_star.cu, kernel_line.cu).
 template <typename T>
-int32_t all_rows_typed(const HostOp& H, bool bpv, std::vector<HostRow>& out) {
-    OpView<T> A(H);
-    const bool upwind = H.d.kind == DEO_OP_UPWIND;
-    const bool nonuni = H.d.nonuniform != 0;
-    const int n = A.n;
-    const int int_first = A.bpc + 1;
-    const int int_last = upwind ? n - A.bpc - A.off : n - A.bpc;
-    RowSink<T> S;
-    S.n = n;
-    if (!upwind) centered_left(A, S); else if (!nonuni) upwind_u_left(A, S); else upwind_n_left(A, S);
-    for (int i = int_first; i <= int_last; ++i) {
-        if (!upwind) centered_interior_row(A, S, i, bpv);
-        else if (!nonuni) upwind_u_interior_row(A, S, i);
-        else upwind_n_interior_row(A, S, i);
+struct RowGenT final : RowGenerator {
+    OpView<T> A;
+    bool upwind, nonuni, bpv, good = true;
+    int int_first, int_last;
+    RowSink<T> edges;     // left and right rows (a handful)
+    RowGenT(const HostOp& H, bool bpv_) : A(H), upwind(H.d.kind == DEO_OP_UPWIND), nonuni(H.d.nonuniform != 0), bpv(bpv_) {
+        n = A.n;
+        int_first = A.bpc + 1;
+        int_last = upwind ? n - A.bpc - A.off : n - A.bpc;
+        edges.n = n;
+        // the three parts must not overlap (tiny grids replay "later writers win" in build_op instead)
+        if (int_last < int_first || A.bpc + A.n_high() + 1 > n) { good = false; return; }
+        if (!upwind) centered_left(A, edges); else if (!nonuni) upwind_u_left(A, edges); else upwind_n_left(A, edges);
+        if (!upwind) centered_right(A, edges, bpv); else if (!nonuni) upwind_u_right(A, edges); else upwind_n_right(A, edges);
+        good = edges.ok;
+        bool constc = true;
+        for (int i = 1; i < n; ++i) constc = constc && (memcmp(&A.coeff[i], &A.coeff[0], sizeof(T)) == 0);
+        interior_uniform = !nonuni && constc;
     }
-    if (!upwind) centered_right(A, S, bpv); else if (!nonuni) upwind_u_right(A, S); else upwind_n_right(A, S);
-    DEO_REQUIRE(S.ok, "op on axis %d (len %d): %s", H.d.axis, n, S.why.c_str());
-    out.assign((size_t)n, HostRow{});
-    for (int i = 1; i <= n; ++i) {
-        auto it = S.rows.find(i);
-        DEO_REQUIRE(it != S.rows.end(), "op on axis %d (len %d): row %d is written by no convolution", H.d.axis, n, i);
-        HostRow& r = out[(size_t)i - 1];
-        r.start = it->second.start;
-        r.ntaps = it->second.ntaps;
-        for (int k = 0; k < kMaxBTaps; ++k) r.w[k] = k < r.ntaps ? (double)it->second.w[k] : 0.0;
+    bool ok() const override { return good; }
+    bool row(int r0, HostRow& out) override {
+        const int i = r0 + 1;
+        const RowSpec<T>* spec = nullptr;
+        RowSink<T> one;
+        if (i >= int_first && i <= int_last) {
+            one.n = n;
+            if (!upwind) centered_interior_row(A, one, i, bpv);
+            else if (!nonuni) upwind_u_interior_row(A, one, i);
+            else upwind_n_interior_row(A, one, i);
+            if (!one.ok) return false;
+            spec = &one.rows[i];
+        } else {
+            auto it = edges.rows.find(i);
+            if (it == edges.rows.end()) return false;
+            spec = &it->second;
+        }
+        out.start = spec->start;
+        out.ntaps = spec->ntaps;
+        for (int k = 0; k < kMaxBTaps; ++k) out.w[k] = k < spec->ntaps ? (double)spec->w[k] : 0.0;
+        return true;
     }
-    return DEO_OK;
-}
+};
 
 }  // namespace
 
-int32_t plan_all_rows(const deo_plan* plan, int k, std::vector<HostRow>& out) {
+std::unique_ptr<RowGenerator> make_row_generator(const deo_plan* plan, int k) {
     const HostOp& H = plan->ops[(size_t)k];
     const bool bpv = plan->ndims == 1 && plan->bc[H.d.axis].d.kind != DEO_BC_NONE;
-    return plan->dtype == DEO_F64 ? all_rows_typed<double>(H, bpv, out) : all_rows_typed<float>(H, bpv, out);
+    if (plan->dtype == DEO_F64) return std::unique_ptr<RowGenerator>(new RowGenT<double>(H, bpv));
+    return std::unique_ptr<RowGenerator>(new RowGenT<float>(H, bpv));
 }
 
 int32_t build_device_plan(deo_plan* plan) {

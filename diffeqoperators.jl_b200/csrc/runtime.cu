@@ -66,12 +66,16 @@ int32_t deo_init(int32_t device) {
     if (r.ready) {   // switching device: drop old streams
         cudaStreamDestroy(r.stream);
         cudaStreamDestroy(r.comm_stream);
+        cudaStreamDestroy(r.h2d_stream);
+        cudaStreamDestroy(r.d2h_stream);
         r.ready = false;
     }
     DEO_CUDA(cudaStreamCreateWithFlags(&r.stream, cudaStreamNonBlocking));
     int lo = 0, hi = 0;
     DEO_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     DEO_CUDA(cudaStreamCreateWithPriority(&r.comm_stream, cudaStreamNonBlocking, hi));
+    DEO_CUDA(cudaStreamCreateWithFlags(&r.h2d_stream, cudaStreamNonBlocking));
+    DEO_CUDA(cudaStreamCreateWithFlags(&r.d2h_stream, cudaStreamNonBlocking));
     r.device = device;
     r.sm_count = prop.multiProcessorCount;
     r.ready = true;

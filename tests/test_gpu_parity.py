@@ -120,6 +120,43 @@ def test_config1_heat_equation_1d(D, O):
         ud = D.DeviceArray.from_host(u)
         D.mul_(du, A * Qd, ud)
         assert_close(du.to_host(), O.apply_axis(B, u, Qo), np.float64, f"C1 n={n}")
+        plan = D.build_plans(A * Qd, (n,), (n,), np.float64)[0][0]
+        assert plan.info[0] == "line"
+        # single uniform operator: the 1-D kernel keeps the per-point kernel's arithmetic order -> identical bits
+        dg = D.DeviceArray((n,), np.float64)
+        D.mul_(dg, A * Qd, ud, flags=_flags(D, True))
+        assert np.array_equal(dg.to_host(), du.to_host())
+
+
+def test_line_kernel_selection_and_table_mode(D, O):
+    """1-D plans: uniform + constant coefficient -> 'line' (weights in the constant bank); non-uniform grids,
+    coefficient vectors, mixed-sign upwind and sums of operators -> 'line-table' (merged per-row weights);
+    PeriodicBC stays on the per-point kernel."""
+    n = 4099                                                           # odd length: scalar tail stores
+    h = 1.0 / (n + 1)
+    u = uniform_field(n, np.float64, seed=12)
+    Qd, Qo = bc_pair(("robin", (1.0, 0.5, 0.25), (1.0, -0.5, 0.75), 1), h, np.float64)
+    c = np.sin(6 * np.pi * np.arange(1, n + 1) / n)
+    dx = nonuniform_dx(n, h, np.float64)
+    A1, B1 = make_pair("centered", 2, 4, dx, n, 1)
+    A2, B2 = make_pair("upwind", 1, 2, dx, n, c)
+    A3, B3 = make_pair("centered", 1, 4, h, n, 1)
+    for ops, want_kernel in [([(A3, B3)], "line"), ([(A1, B1)], "line-table"), ([(A2, B2)], "line-table"),
+                             ([(A1, B1), (A2, B2), (A3, B3)], "line-table")]:
+        A = ops[0][0]
+        for o in ops[1:]:
+            A = A + o[0]
+        G = A * Qd
+        assert D.build_plans(G, (n,), (n,), np.float64)[0][0].info[0] == want_kernel
+        want = sum(O.apply_axis(b, u, Qo) for _, b in ops)
+        assert_close(G * u, want, np.float64, f"line {want_kernel} {len(ops)} ops")
+    Gp = A3 * D.PeriodicBC(np.float64)
+    assert D.build_plans(Gp, (n,), (n,), np.float64)[0][0].info[0] == "generic"
+    # overwrite = false on the 1-D kernel
+    du0 = uniform_field(n, np.float64, seed=13)
+    dd = D.DeviceArray.from_host(du0)
+    D.mul_(dd, A3 * Qd, D.DeviceArray.from_host(u), overwrite=False)
+    assert_close(dd.to_host(), du0 + O.apply_axis(B3, u, Qo), np.float64, "line accumulate")
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -387,6 +424,35 @@ def test_host_buffer_path_equals_device_path(D):
     host = (A * Q) * u                                        # numpy in -> numpy out (H2D + kernel + D2H)
     dev = ((A * Q) * D.DeviceArray.from_host(u)).to_host()
     assert isinstance(host, np.ndarray) and np.array_equal(host, dev)
+
+
+def test_host_buffer_pipeline_equals_device_path(D, monkeypatch):
+    """deo_plan_apply_host cuts the field into chunks of planes (upload | kernel | download overlapped); with a small
+    chunk size every kernel family goes through several chunks and must reproduce the one-shot device result bitwise."""
+    monkeypatch.setenv("DEO_HOST_CHUNK_BYTES", "4096")
+    cases = []
+    shape3, shape2 = (64, 48, 230), (128, 700)
+    h3, h2 = tuple(1.0 / (s + 1) for s in shape3), tuple(1.0 / (s + 1) for s in shape2)
+    lap3 = D.CenteredDifference[1](2, 4, h3[0], shape3[0]) + D.CenteredDifference[2](2, 4, h3[1], shape3[1]) + D.CenteredDifference[3](2, 4, h3[2], shape3[2])
+    Q3 = D.compose(*D.RobinBC((1.0, 0.5, 0.25), (1.0, -0.5, 0.75), h3, 1, shape3))
+    cases.append(("star", lap3 * Q3, shape3, 0))
+    cases.append(("generic", lap3 * Q3, shape3, _flags(D, True)))
+    c = np.sin(6 * np.pi * np.arange(1, shape3[2] + 1) / shape3[2])
+    up = lap3 + D.UpwindDifference[3](1, 2, h3[2], shape3[2], c)
+    cases.append(("star-table", up * Q3, shape3, 0))
+    lap2 = D.CenteredDifference[1](2, 4, h2[0], shape2[0]) + D.CenteredDifference[2](2, 4, h2[1], shape2[1])
+    Q2 = D.compose(*D.RobinBC((1.0, 0.5, 0.25), (1.0, -0.5, 0.75), h2, 1, shape2))
+    cases.append(("star", lap2 * Q2, shape2, 0))
+    for kern, G, shape, flags in cases:
+        assert D.build_plans(G, shape, shape, np.float64, flags=flags)[0][0].info[0] == kern
+        u = uniform_field(shape, np.float64, seed=len(shape))
+        dev = D.DeviceArray(shape, np.float64)
+        D.mul_(dev, G, D.DeviceArray.from_host(u), flags=flags)
+        host = np.zeros(shape, order="F")
+        D.mul_(host, G, u, flags=flags)
+        assert np.array_equal(host, dev.to_host()), kern
+        D.mul_(host, G, u, flags=flags)               # second call reuses the staging buffers
+        assert np.array_equal(host, dev.to_host()), kern
 
 
 def test_small_grids_and_errors(D, O):
