@@ -286,6 +286,7 @@ int32_t star_configure(deo_plan* plan) {
     cfg->zchunk_pref = 64;
     cfg->zchunk_max = getenv("DEO_STAR_ZCHUNK") ? atoi(getenv("DEO_STAR_ZCHUNK")) : 32;
     cfg->l2promo = getenv("DEO_TMA_L2PROMO") ? atoi(getenv("DEO_TMA_L2PROMO")) : 3;
+    cfg->group = getenv("DEO_STAR_GROUP") ? atoi(getenv("DEO_STAR_GROUP")) : -1;   // measured: the plain order is fastest
 
     // ---- CONST eligibility ----
     bool const_ok = plan->ops.size() <= 3 && !getenv("DEO_STAR_FORCE_TABLE");

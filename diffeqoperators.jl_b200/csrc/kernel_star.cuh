@@ -63,6 +63,7 @@ struct StarConfig {
     int zchunk_pref = 0;
     int zchunk_max = 0;      // experiments (DEO_STAR_ZCHUNK): upper bound on the planes per CTA along the march axis
     int l2promo = 3;         // CUtensorMapL2promotion of the tensor map (DEO_TMA_L2PROMO)
+    int group = -1;          // tiles per launch-order group (0: one wave; < 0: plain order) (DEO_STAR_GROUP)
     int sm_count = 0;
 };
 
@@ -194,7 +195,7 @@ __device__ __forceinline__ void load_x_halo(const T* own, T (&xw)[Vec<T>::N + 2 
 template <typename T, int R, int PY, int NWY, bool MID, int MASK, bool TABLE>
 __global__ void __launch_bounds__(NWY * 32, ((PY <= 2 && NWY <= 8) ? 2 : 1))
 k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarParams<T, R> S,
-       const T* __restrict__ u, T* __restrict__ du, int z_begin, int z_end, int zchunk) {
+       const T* __restrict__ u, T* __restrict__ du, int z_begin, int z_end, int zchunk, int tiles_x, int tiles_xy, int group) {
     using G = StarGeom<T, R, PY, NWY, MID>;
     constexpr int VEC = G::VEC, HX = G::HX, PITCH = G::PITCH, NS = G::NS, NQ = G::NQ, TB = 2 * R + 2;
     constexpr int XW = VEC + 2 * R;                        // x window of one vector: coordinates gx-R .. gx+VEC-1+R
@@ -211,9 +212,22 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
     T* const sWz = sWy + G::TY * NQ;                       // TABLE: [zc1 - zc0][NQ] march-axis rows of this chunk
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tx0 = blockIdx.x * G::TX;
-    const int ty0 = MID ? blockIdx.y * G::TY : 0;
-    const int zc0 = z_begin + blockIdx.z * zchunk;
+    // Launch order: tiles are taken in groups of `group` consecutive tiles; inside a group the march-axis chunk is the
+    // slow index.  group == all tiles is the plain order (every tile of chunk 0, then chunk 1, ...), which measured
+    // fastest on B200; smaller groups (a tile's chunks about one wave apart, so that the 2R planes two consecutive
+    // chunks share could hit in L2) were 8 % slower on the 1024^3 case and are kept as an experiment knob only.
+    int tile, chunk;
+    {
+        const int lin = blockIdx.x, nchunks = (z_end - z_begin + zchunk - 1) / zchunk;
+        const int per_group = group * nchunks;
+        const int g = lin / per_group, rem = lin - g * per_group;
+        const int gsz = min(group, tiles_xy - g * group);
+        chunk = rem / gsz;
+        tile = g * group + (rem - chunk * gsz);
+    }
+    const int tx0 = (tile % tiles_x) * G::TX;
+    const int ty0 = MID ? (tile / tiles_x) * G::TY : 0;
+    const int zc0 = z_begin + chunk * zchunk;
     const int zc1 = min(zc0 + zchunk, z_end);
     if (zc0 >= zc1) return;
     const int p_first = zc0 - R;                           // first plane streamed (local index)
@@ -702,8 +716,13 @@ int32_t launch_variant(const StarConfig& C, const void* u, void* du, long long z
         }
         if (TABLE && zc > G::TAB_ZMAX) { set_error("star kernel: march-axis range too short to chunk"); return DEO_ERR_UNSUPPORTED; }
     }
-    dim3 grid((unsigned)((S.nx + G::TX - 1) / G::TX), (unsigned)(MID ? (S.ny + G::TY - 1) / G::TY : 1), (unsigned)((len + zc - 1) / zc));
-    kern<<<grid, G::THREADS, SMEM, s>>>(map, S, (const T*)u, (T*)du, (int)z0, (int)z1, (int)zc);
+    const long long tiles_x = (S.nx + G::TX - 1) / G::TX, nchunks = (len + zc - 1) / zc;
+    const long long slots_all = (long long)C.sm_count * G::CTAS_PER_SM;
+    long long group = C.group > 0 ? C.group : (slots_all >= tiles_x ? slots_all / tiles_x * tiles_x : slots_all);
+    if (C.group < 0 || group > tiles) group = tiles;                       // legacy order: all tiles of a chunk, then the next chunk
+    DEO_REQUIRE(tiles * nchunks < (1LL << 31), "star kernel: grid too large");
+    kern<<<(unsigned)(tiles * nchunks), G::THREADS, SMEM, s>>>(map, S, (const T*)u, (T*)du, (int)z0, (int)z1, (int)zc, (int)tiles_x, (int)tiles,
+                                                               (int)group);
     DEO_CUDA(cudaGetLastError());
     return DEO_OK;
 }

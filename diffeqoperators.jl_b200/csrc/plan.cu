@@ -234,9 +234,15 @@ int32_t deo_plan_apply_host(deo_plan* plan, void* du_host, const void* u_host) {
     long long chunk = (long long)(chunk_bytes / (out_plane ? out_plane : 1));
     if (chunk < 2 * reach + 8) chunk = 2 * reach + 8;
     const bool rangeable = plan->ndims == 3 || (plan->ndims == 2 && plan->star);   // kernels that take a range of the last axis
-    const long long nchunks = rangeable ? (nlast + chunk - 1) / chunk : 1;
-    const bool pipelined = nchunks >= 3 && !plan->padded[last] && plan->bc[last].d.kind != DEO_BC_PERIODIC &&
-                           nlast - (nchunks - 1) * chunk >= 2 * reach + 2;
+    // chunk boundaries: equal chunks, a short remainder is merged into the last one (a chunk must hold the one-sided rows)
+    std::vector<long long> zb;
+    if (rangeable && !plan->padded[last] && plan->bc[last].d.kind != DEO_BC_PERIODIC) {
+        for (long long z = 0; z < nlast; z += chunk) zb.push_back(z);
+        if (zb.size() > 1 && nlast - zb.back() < 2 * reach + 2) zb.pop_back();
+        zb.push_back(nlast);
+    }
+    const long long nchunks = zb.empty() ? 1 : (long long)zb.size() - 1;
+    const bool pipelined = nchunks >= 3;
     if (!pipelined) {
         DEO_CUDA(cudaMemcpyAsync(u->ptr, u_host, in_b, cudaMemcpyHostToDevice, s));
         if (plan->accumulate) DEO_CUDA(cudaMemcpyAsync(du->ptr, du_host, out_b, cudaMemcpyHostToDevice, s));
@@ -255,7 +261,7 @@ int32_t deo_plan_apply_host(deo_plan* plan, void* du_host, const void* u_host) {
     DEO_CUDA(cudaStreamSynchronize(s));
     // stage 1: uploads, in order, on the upload stream
     for (long long k = 0; k < nchunks; ++k) {
-        const long long z0 = k * chunk, z1 = (k + 1) * chunk < nlast ? (k + 1) * chunk : nlast;
+        const long long z0 = zb[(size_t)k], z1 = zb[(size_t)k + 1];
         DEO_CUDA(cudaMemcpyAsync((char*)u->ptr + (size_t)z0 * in_plane, (const char*)u_host + (size_t)z0 * in_plane, (size_t)(z1 - z0) * in_plane,
                                  cudaMemcpyHostToDevice, R.h2d_stream));
         if (plan->accumulate)
@@ -265,7 +271,7 @@ int32_t deo_plan_apply_host(deo_plan* plan, void* du_host, const void* u_host) {
     }
     // stages 2 and 3: kernel on chunk k once chunk k+1 has landed, download behind it
     for (long long k = 0; k < nchunks; ++k) {
-        const long long z0 = k * chunk, z1 = (k + 1) * chunk < nlast ? (k + 1) * chunk : nlast;
+        const long long z0 = zb[(size_t)k], z1 = zb[(size_t)k + 1];
         DEO_CUDA(cudaStreamWaitEvent(s, plan->host_ev[(size_t)(k + 1 < nchunks ? k + 1 : k)], 0));
         if (plan->ndims == 3) rc = launch_plan(plan, du->ptr, u->ptr, z0, z1, s);
         else rc = launch_star(plan, du->ptr, u->ptr, z0, z1, s, true);     // 2-D: a range of rows of the last axis
