@@ -15,6 +15,8 @@
 // bundled one) shares it; nothing here links against libnccl.
 #include <dlfcn.h>
 
+#include <cstdlib>
+
 #include "common.hpp"
 
 namespace deo {
@@ -85,7 +87,14 @@ struct deo_dist {
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
     cudaEvent_t ev_ready = nullptr, ev_halo = nullptr;
+    int* halo_flag = nullptr;      // device word: index of the last application whose halo planes have landed
+    int halo_step = 0;
 };
+
+__global__ void k_publish_halo(int* flag, int step) {
+    __threadfence();
+    *reinterpret_cast<volatile int*>(flag) = step;
+}
 
 namespace {
 
@@ -186,6 +195,20 @@ int32_t dist_apply(deo_plan* plan, deo_buffer* du, deo_buffer* u) {
         DEO_NCCL(N.Recv(base + (size_t)(cnt + H) * plane * es, (size_t)H * plane, dt, hi, ctx->comm, R.comm_stream));  // high halo
     }
     DEO_NCCL(N.GroupEnd());
+    // One launch for the whole slab when the tiled kernel can take it: the chunks that read halo planes are scheduled
+    // last and wait in the kernel for the flag the communication stream publishes here.
+    if (plan->star && !getenv("DEO_DIST_NO_FUSED")) {
+        const int step = ++ctx->halo_step;
+        k_publish_halo<<<1, 1, 0, R.comm_stream>>>(ctx->halo_flag, step);
+        DEO_CUDA(cudaGetLastError());
+        const int32_t frc = launch_star_fused(plan, du->ptr, u->ptr, cnt, R.stream, ctx->halo_flag, step, (has_lo ? 1 : 0) | (has_hi ? 2 : 0));
+        if (frc == DEO_OK) {
+            g_launches += 1;
+            // the next exchange may overwrite the halo planes only after this launch; nothing else to order
+            return DEO_OK;
+        }
+        if (frc != DEO_ERR_UNSUPPORTED) return frc;
+    }
     DEO_CUDA(cudaEventRecord(ctx->ev_halo, R.comm_stream));
     // planes that read no halo run concurrently with the exchange
     const long long z_lo = has_lo ? (H < cnt ? H : cnt) : 0;
@@ -238,6 +261,8 @@ int32_t deo_dist_init(const void* id_bytes, int32_t rank, int32_t nranks, deo_di
     ctx->nranks = nranks;
     DEO_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming));
     DEO_CUDA(cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming));
+    DEO_CUDA(cudaMalloc(&ctx->halo_flag, sizeof(int)));
+    DEO_CUDA(cudaMemset(ctx->halo_flag, 0, sizeof(int)));
     *out = ctx.release();
     return DEO_OK;
 }
@@ -248,6 +273,7 @@ int32_t deo_dist_destroy(deo_dist* ctx) {
     if (ctx->comm) nccl().CommDestroy(ctx->comm);
     if (ctx->ev_ready) cudaEventDestroy(ctx->ev_ready);
     if (ctx->ev_halo) cudaEventDestroy(ctx->ev_halo);
+    if (ctx->halo_flag) cudaFree(ctx->halo_flag);
     delete ctx;
     return DEO_OK;
 }

@@ -397,4 +397,18 @@ int32_t launch_star(const deo_plan* plan, void* du, const void* u, long long z0,
     return plan->dtype == DEO_F64 ? dispatch_T<double>(C, u, du, z0, z1, s) : dispatch_T<float>(C, u, du, z0, z1, s);
 }
 
+// Slab plans: ONE launch over all own planes; the CTAs of the first / last march-axis chunk (scheduled last) wait in the
+// kernel until *halo_flag >= expect, which the communication stream publishes after the neighbour exchange has landed.
+// Returns DEO_ERR_UNSUPPORTED when the slab is too thin to chunk (the caller then uses the three-launch schedule).
+int32_t launch_star_fused(const deo_plan* plan, void* du, const void* u, long long cnt, cudaStream_t s, const int* halo_flag, int expect, int sides) {
+    StarConfig& C = *static_cast<StarConfig*>(plan->star.get());
+    if (!C.mid) return DEO_ERR_UNSUPPORTED;
+    const long long zmax = C.zchunk_max > 0 ? C.zchunk_max : cnt;
+    if (cnt < 3 * zmax + 4 * C.R + 4) return DEO_ERR_UNSUPPORTED;          // at least 3 chunks whatever the chunk search picks
+    C.halo_flag = halo_flag; C.halo_expect = expect; C.halo_sides = sides;
+    const int32_t rc = launch_star(plan, du, u, 0, cnt, s, false);
+    C.halo_flag = nullptr;
+    return rc;
+}
+
 }  // namespace deo

@@ -63,6 +63,8 @@ struct StarConfig {
     int zchunk_pref = 0;
     int zchunk_max = 0;      // experiments (DEO_STAR_ZCHUNK): upper bound on the planes per CTA along the march axis
     int l2promo = 3;         // CUtensorMapL2promotion of the tensor map (DEO_TMA_L2PROMO)
+    const int* halo_flag = nullptr;   // per launch (slab plans): device word the communication stream sets to halo_expect
+    int halo_expect = 0, halo_sides = 0;
     int group = -1;          // tiles per launch-order group (0: one wave; < 0: plain order) (DEO_STAR_GROUP)
     int sm_count = 0;
 };
@@ -195,7 +197,8 @@ __device__ __forceinline__ void load_x_halo(const T* own, T (&xw)[Vec<T>::N + 2 
 template <typename T, int R, int PY, int NWY, bool MID, int MASK, bool TABLE>
 __global__ void __launch_bounds__(NWY * 32, ((PY <= 2 && NWY <= 8) ? 2 : 1))
 k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarParams<T, R> S,
-       const T* __restrict__ u, T* __restrict__ du, int z_begin, int z_end, int zchunk, int tiles_x, int tiles_xy, int group) {
+       const T* __restrict__ u, T* __restrict__ du, int z_begin, int z_end, int zchunk, int tiles_x, int tiles_xy, int group,
+       const int* __restrict__ halo_flag, int halo_expect, int halo_sides) {
     using G = StarGeom<T, R, PY, NWY, MID>;
     constexpr int VEC = G::VEC, HX = G::HX, PITCH = G::PITCH, NS = G::NS, NQ = G::NQ, TB = 2 * R + 2;
     constexpr int XW = VEC + 2 * R;                        // x window of one vector: coordinates gx-R .. gx+VEC-1+R
@@ -224,6 +227,9 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
         const int gsz = min(group, tiles_xy - g * group);
         chunk = rem / gsz;
         tile = g * group + (rem - chunk * gsz);
+        // slab plans (one launch for the whole slab): the first and last chunk read halo planes that arrive over NVLink
+        // while the launch is running -- they are scheduled last (plain order only; the host guarantees nchunks >= 3)
+        if (halo_flag != nullptr) chunk = chunk < nchunks - 2 ? chunk + 1 : (chunk == nchunks - 2 ? 0 : nchunks - 1);
     }
     const int tx0 = (tile % tiles_x) * G::TX;
     const int ty0 = MID ? (tile / tiles_x) * G::TY : 0;
@@ -250,6 +256,18 @@ k_star(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPar
     if (threadIdx.x == 0) {
         for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NWY); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (halo_flag != nullptr && (((halo_sides & 1) && zc0 - R < z_begin) || ((halo_sides & 2) && zc1 + R > z_end))) {
+            // wait until the communication stream has published this application's halo planes (bounded: a lost
+            // exchange must fail loudly, never hang the GPU)
+            int seen, spins = 0;
+            do {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(halo_flag) : "memory");
+                if (seen - halo_expect >= 0) break;
+                __nanosleep(200);
+            } while (++spins < (1 << 24));
+            if (seen - halo_expect < 0) __trap();
+            asm volatile("fence.proxy.async;" ::: "memory");
+        }
         for (int k0 = 0; k0 < NS && k0 < n_planes; ++k0) issue_plane(k0);
     }
     if constexpr (TABLE) {
@@ -720,9 +738,14 @@ int32_t launch_variant(const StarConfig& C, const void* u, void* du, long long z
     const long long slots_all = (long long)C.sm_count * G::CTAS_PER_SM;
     long long group = C.group > 0 ? C.group : (slots_all >= tiles_x ? slots_all / tiles_x * tiles_x : slots_all);
     if (C.group < 0 || group > tiles) group = tiles;                       // legacy order: all tiles of a chunk, then the next chunk
+    const bool fused = C.halo_flag != nullptr;                             // slab launch that waits for its halo planes in the kernel
+    if (fused) {
+        group = tiles;
+        if (nchunks < 3) { set_error("star kernel: fused halo launch needs at least 3 chunks"); return DEO_ERR_UNSUPPORTED; }
+    }
     DEO_REQUIRE(tiles * nchunks < (1LL << 31), "star kernel: grid too large");
     kern<<<(unsigned)(tiles * nchunks), G::THREADS, SMEM, s>>>(map, S, (const T*)u, (T*)du, (int)z0, (int)z1, (int)zc, (int)tiles_x, (int)tiles,
-                                                               (int)group);
+                                                               (int)group, fused ? C.halo_flag : nullptr, C.halo_expect, C.halo_sides);
     DEO_CUDA(cudaGetLastError());
     return DEO_OK;
 }
