@@ -270,6 +270,7 @@ def main():
     ap.add_argument("--workload", default="C5", choices=sorted(WORKLOADS))
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--nz", type=int, default=0, help="override the last extent of the workload (experiments; not a BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--force-generic", action="store_true", help="run the per-point kernel instead of the tiled one (A/B)")
     args = ap.parse_args()
@@ -314,8 +315,11 @@ def main():
     if N > 1 and len(shape) != 3:
         raise SystemExit("multi-GPU runs use a 3-D workload (slabs along dim 3)")
     gshape = tuple(shape)
+    if args.nz > 0:
+        gshape = gshape[:-1] + (args.nz,)
+        desc += f" [last extent overridden to {args.nz}]"
     if args.scaling == "weak" and N > 1:
-        gshape = shape[:-1] + (shape[-1] * N,)
+        gshape = gshape[:-1] + (gshape[-1] * N,)
     es = np.dtype(dtype).itemsize
     flags = _lib.DEO_FLAG_FORCE_GENERIC if args.force_generic else 0
     G = build_operator(D, name, gshape, dtype)

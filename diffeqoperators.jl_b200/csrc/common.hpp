@@ -204,7 +204,11 @@ int32_t launch_generic(const deo_plan* plan, void* du, const void* u, long long 
 // kernel_star.cu
 int32_t star_configure(deo_plan* plan);
 int32_t launch_star(const deo_plan* plan, void* du, const void* u, long long z0, long long z1, cudaStream_t s, bool explicit_range = false);
+struct StarLimits { bool fusable = false; long long min_fused_planes = 0; };
+StarLimits star_limits(const deo_plan* plan);
 int32_t launch_star_fused(const deo_plan* plan, void* du, const void* u, long long cnt, cudaStream_t s, const int* halo_flag, int expect, int sides);
+// dist.cu
+void dist_forget_buffer(void* ptr);
 // kernel_line.cu
 int32_t line_configure(deo_plan* plan);
 int32_t launch_line(const deo_plan* plan, void* du, const void* u, cudaStream_t s);

@@ -13,9 +13,11 @@
 //
 // NCCL is bound at run time with dlopen so that a process that already carries an NCCL (torch's
 // bundled one) shares it; nothing here links against libnccl.
+#include <cuda.h>
 #include <dlfcn.h>
 
 #include <cstdlib>
+#include <map>
 
 #include "common.hpp"
 
@@ -83,18 +85,91 @@ int32_t nccl_fail(ncclResult_t r, const char* what) {
     } while (0)
 }  // namespace
 
+// Flag words of one rank (device memory, exported to both slab neighbours through CUDA IPC).  All values are
+// application indices (monotonic per context).
+enum { F_HALO_FROM_LOW = 0,   // the low neighbour's planes for application i have landed in my low halo
+       F_HALO_FROM_HIGH = 1,  // same from the high neighbour
+       F_LOW_DONE = 2,        // the low neighbour has finished application i (its halo planes may be overwritten)
+       F_HIGH_DONE = 3,
+       F_STEPWORD = 4,        // staging words: values copied into the neighbours' flags by the copy engines
+       F_ACKWORD = 5,
+       F_COUNT = 16 };
+
+struct PeerField { void* lo = nullptr; void* hi = nullptr; };
+
 struct deo_dist {
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
     cudaEvent_t ev_ready = nullptr, ev_halo = nullptr;
-    int* halo_flag = nullptr;      // device word: index of the last application whose halo planes have landed
-    int halo_step = 0;
+    // peer-to-peer halo exchange over NVLink (copy engines, no kernels): see dist_apply
+    bool p2p = false;
+    int* flags = nullptr;                  // F_COUNT ints
+    int *lo_flags = nullptr, *hi_flags = nullptr;   // the neighbours' flag arrays, mapped
+    unsigned char* xbuf = nullptr;         // 3 x 64 bytes device staging for the handle exchange
+    std::map<void*, PeerField> fields;     // my field buffer -> the neighbours' mappings of theirs
+    int step = 0;
 };
 
-__global__ void k_publish_halo(int* flag, int step) {
-    __threadfence();
-    *reinterpret_cast<volatile int*>(flag) = step;
+namespace deo {
+// live contexts, so that freeing a field buffer drops the neighbours' mappings registered under its address
+static std::vector<deo_dist*> g_contexts;
+void dist_forget_buffer(void* ptr) {
+    for (deo_dist* c : g_contexts) {
+        auto it = c->fields.find(ptr);
+        if (it == c->fields.end()) continue;
+        cudaStreamSynchronize(rt().comm_stream);
+        if (it->second.lo) cudaIpcCloseMemHandle(it->second.lo);
+        if (it->second.hi) cudaIpcCloseMemHandle(it->second.hi);
+        c->fields.erase(it);
+    }
 }
+}  // namespace deo
+
+namespace {
+
+typedef CUresult (*PFN_streamValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+PFN_streamValue32 stream_op(const char* name) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) return (PFN_streamValue32)p;
+    return nullptr;
+}
+PFN_streamValue32 wait_value32() { static PFN_streamValue32 f = stream_op("cuStreamWaitValue32"); return f; }
+PFN_streamValue32 write_value32() { static PFN_streamValue32 f = stream_op("cuStreamWriteValue32"); return f; }
+
+// Neighbours swap one 64-byte CUDA IPC handle each way (through NCCL, the only channel the library has); collective
+// over the slab neighbours, synchronous.  lo/hi are left untouched where there is no neighbour.
+int32_t swap_handles(deo_dist* ctx, const cudaIpcMemHandle_t& mine, cudaIpcMemHandle_t* lo, cudaIpcMemHandle_t* hi) {
+    NcclApi& N = nccl();
+    cudaStream_t cs = rt().comm_stream;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    DEO_CUDA(cudaMemcpyAsync(ctx->xbuf, &mine, 64, cudaMemcpyHostToDevice, cs));
+    const bool has_lo = ctx->rank > 0, has_hi = ctx->rank + 1 < ctx->nranks;
+    DEO_NCCL(N.GroupStart());
+    if (has_lo) { DEO_NCCL(N.Send(ctx->xbuf, 64, ncclUint8, ctx->rank - 1, ctx->comm, cs)); DEO_NCCL(N.Recv(ctx->xbuf + 64, 64, ncclUint8, ctx->rank - 1, ctx->comm, cs)); }
+    if (has_hi) { DEO_NCCL(N.Send(ctx->xbuf, 64, ncclUint8, ctx->rank + 1, ctx->comm, cs)); DEO_NCCL(N.Recv(ctx->xbuf + 128, 64, ncclUint8, ctx->rank + 1, ctx->comm, cs)); }
+    DEO_NCCL(N.GroupEnd());
+    unsigned char host[192];
+    DEO_CUDA(cudaMemcpyAsync(host, ctx->xbuf, 192, cudaMemcpyDeviceToHost, cs));
+    DEO_CUDA(cudaStreamSynchronize(cs));
+    if (has_lo) memcpy(lo, host + 64, 64);
+    if (has_hi) memcpy(hi, host + 128, 64);
+    return DEO_OK;
+}
+
+// Maps the neighbours' copies of one exported allocation.  Collective over the slab neighbours.
+int32_t map_neighbours(deo_dist* ctx, void* mine, void** lo, void** hi) {
+    cudaIpcMemHandle_t hm, hl, hh;
+    DEO_CUDA(cudaIpcGetMemHandle(&hm, mine));
+    int32_t rc = swap_handles(ctx, hm, &hl, &hh);
+    if (rc) return rc;
+    *lo = *hi = nullptr;
+    if (ctx->rank > 0) DEO_CUDA(cudaIpcOpenMemHandle(lo, hl, cudaIpcMemLazyEnablePeerAccess));
+    if (ctx->rank + 1 < ctx->nranks) DEO_CUDA(cudaIpcOpenMemHandle(hi, hh, cudaIpcMemLazyEnablePeerAccess));
+    return DEO_OK;
+}
+
+}  // namespace
 
 namespace {
 
@@ -182,6 +257,54 @@ int32_t dist_apply(deo_plan* plan, deo_buffer* du, deo_buffer* u) {
     char* base = (char*)u->ptr;
     const int lo = plan->rank - 1, hi = plan->rank + 1;
     const bool has_lo = lo >= 0, has_hi = hi < plan->nranks;
+    // ---- fused schedule: peer-to-peer halo pushes by the copy engines + ONE kernel launch for the whole slab ----------
+    // The halo planes go straight into the neighbours' field buffers (mapped through CUDA IPC) over NVLink, followed by
+    // a 4-byte flag; no kernel takes part in the exchange, so it cannot compete with the stencil kernel for SM slots.
+    // The stencil kernel's first / last march-axis chunks are scheduled last and wait in the kernel for the flag
+    // (kernel_star.cuh).  Before overwriting a neighbour's halo planes the stream waits (cuStreamWaitValue32) until that
+    // neighbour has reported the previous application finished.  Every rank takes the same decision (global extents).
+    {
+        const StarLimits lim = star_limits(plan);
+        const long long min_cnt = plan->dims[plan->slab_axis] / plan->nranks;
+        if (ctx->p2p && plan->star && u->owned && lim.fusable && min_cnt >= lim.min_fused_planes && !getenv("DEO_DIST_NO_FUSED")) {
+            auto it = ctx->fields.find(u->ptr);
+            if (it == ctx->fields.end()) {                       // first use of this field buffer: collective registration
+                DEO_CUDA(cudaStreamSynchronize(R.stream));
+                PeerField pf;
+                int32_t rc = map_neighbours(ctx, u->ptr, &pf.lo, &pf.hi);
+                if (rc) return rc;
+                it = ctx->fields.emplace(u->ptr, pf).first;
+            }
+            const PeerField& pf = it->second;
+            const int step = ++ctx->step;
+            const size_t plane_b = plane * es;
+            CUstream cs = (CUstream)R.comm_stream;
+            DEO_CUDA(cudaEventRecord(ctx->ev_ready, R.stream));
+            DEO_CUDA(cudaStreamWaitEvent(R.comm_stream, ctx->ev_ready, 0));
+            if (has_lo) {
+                int64_t s_lo = 0, c_lo = 0;
+                deo_dist_slab(plan->dims[plan->slab_axis], plan->nranks, lo, &s_lo, &c_lo);
+                if (wait_value32()(cs, (CUdeviceptr)(ctx->flags + F_LOW_DONE), (cuuint32_t)(step - 1), CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) { set_error("cuStreamWaitValue32 failed"); return DEO_ERR_CUDA; }
+                DEO_CUDA(cudaMemcpyAsync((char*)pf.lo + (size_t)(H + c_lo) * plane_b, base + (size_t)H * plane_b, (size_t)H * plane_b, cudaMemcpyDefault, R.comm_stream));
+            }
+            if (has_hi) {
+                if (wait_value32()(cs, (CUdeviceptr)(ctx->flags + F_HIGH_DONE), (cuuint32_t)(step - 1), CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) { set_error("cuStreamWaitValue32 failed"); return DEO_ERR_CUDA; }
+                DEO_CUDA(cudaMemcpyAsync((char*)pf.hi, base + (size_t)cnt * plane_b, (size_t)H * plane_b, cudaMemcpyDefault, R.comm_stream));
+            }
+            if (write_value32()(cs, (CUdeviceptr)(ctx->flags + F_STEPWORD), (cuuint32_t)step, CU_STREAM_WRITE_VALUE_DEFAULT) != CUDA_SUCCESS) { set_error("cuStreamWriteValue32 failed"); return DEO_ERR_CUDA; }
+            if (has_lo) DEO_CUDA(cudaMemcpyAsync(ctx->lo_flags + F_HALO_FROM_HIGH, ctx->flags + F_STEPWORD, sizeof(int), cudaMemcpyDefault, R.comm_stream));
+            if (has_hi) DEO_CUDA(cudaMemcpyAsync(ctx->hi_flags + F_HALO_FROM_LOW, ctx->flags + F_STEPWORD, sizeof(int), cudaMemcpyDefault, R.comm_stream));
+            int32_t rc = launch_star_fused(plan, du->ptr, u->ptr, cnt, R.stream, ctx->flags, step, (has_lo ? 1 : 0) | (has_hi ? 2 : 0));
+            if (rc) return rc;
+            g_launches += 1;
+            // tell the neighbours this application is finished here (they may overwrite my halo planes)
+            CUstream ks = (CUstream)R.stream;
+            if (write_value32()(ks, (CUdeviceptr)(ctx->flags + F_ACKWORD), (cuuint32_t)step, CU_STREAM_WRITE_VALUE_DEFAULT) != CUDA_SUCCESS) { set_error("cuStreamWriteValue32 failed"); return DEO_ERR_CUDA; }
+            if (has_lo) DEO_CUDA(cudaMemcpyAsync(ctx->lo_flags + F_HIGH_DONE, ctx->flags + F_ACKWORD, sizeof(int), cudaMemcpyDefault, R.stream));
+            if (has_hi) DEO_CUDA(cudaMemcpyAsync(ctx->hi_flags + F_LOW_DONE, ctx->flags + F_ACKWORD, sizeof(int), cudaMemcpyDefault, R.stream));
+            return DEO_OK;
+        }
+    }
     // exchange on the communication stream, after everything already queued on the compute stream (u may be its output)
     DEO_CUDA(cudaEventRecord(ctx->ev_ready, R.stream));
     DEO_CUDA(cudaStreamWaitEvent(R.comm_stream, ctx->ev_ready, 0));
@@ -195,20 +318,6 @@ int32_t dist_apply(deo_plan* plan, deo_buffer* du, deo_buffer* u) {
         DEO_NCCL(N.Recv(base + (size_t)(cnt + H) * plane * es, (size_t)H * plane, dt, hi, ctx->comm, R.comm_stream));  // high halo
     }
     DEO_NCCL(N.GroupEnd());
-    // One launch for the whole slab when the tiled kernel can take it: the chunks that read halo planes are scheduled
-    // last and wait in the kernel for the flag the communication stream publishes here.
-    if (plan->star && !getenv("DEO_DIST_NO_FUSED")) {
-        const int step = ++ctx->halo_step;
-        k_publish_halo<<<1, 1, 0, R.comm_stream>>>(ctx->halo_flag, step);
-        DEO_CUDA(cudaGetLastError());
-        const int32_t frc = launch_star_fused(plan, du->ptr, u->ptr, cnt, R.stream, ctx->halo_flag, step, (has_lo ? 1 : 0) | (has_hi ? 2 : 0));
-        if (frc == DEO_OK) {
-            g_launches += 1;
-            // the next exchange may overwrite the halo planes only after this launch; nothing else to order
-            return DEO_OK;
-        }
-        if (frc != DEO_ERR_UNSUPPORTED) return frc;
-    }
     DEO_CUDA(cudaEventRecord(ctx->ev_halo, R.comm_stream));
     // planes that read no halo run concurrently with the exchange
     const long long z_lo = has_lo ? (H < cnt ? H : cnt) : 0;
@@ -261,19 +370,35 @@ int32_t deo_dist_init(const void* id_bytes, int32_t rank, int32_t nranks, deo_di
     ctx->nranks = nranks;
     DEO_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming));
     DEO_CUDA(cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming));
-    DEO_CUDA(cudaMalloc(&ctx->halo_flag, sizeof(int)));
-    DEO_CUDA(cudaMemset(ctx->halo_flag, 0, sizeof(int)));
+    // peer-to-peer exchange state; any failure here (IPC not permitted, stream memory operations missing) leaves the
+    // NCCL send/recv schedule in charge
+    if (!getenv("DEO_DIST_NO_P2P") && wait_value32() && write_value32() && nranks > 1) {
+        bool ok = cudaMalloc(&ctx->flags, F_COUNT * sizeof(int)) == cudaSuccess && cudaMemset(ctx->flags, 0, F_COUNT * sizeof(int)) == cudaSuccess &&
+                  cudaMalloc(&ctx->xbuf, 192) == cudaSuccess;
+        void *lf = nullptr, *hf = nullptr;
+        ok = ok && cudaDeviceSynchronize() == cudaSuccess && map_neighbours(ctx.get(), ctx->flags, &lf, &hf) == DEO_OK;
+        ctx->lo_flags = (int*)lf;
+        ctx->hi_flags = (int*)hf;
+        ctx->p2p = ok;
+        if (!ok) cudaGetLastError();
+    }
     *out = ctx.release();
+    g_contexts.push_back(*out);
     return DEO_OK;
 }
 
 int32_t deo_dist_destroy(deo_dist* ctx) {
     if (!ctx) return DEO_OK;
     deo_sync();
+    for (size_t i = 0; i < g_contexts.size(); ++i) if (g_contexts[i] == ctx) { g_contexts.erase(g_contexts.begin() + (long)i); break; }
     if (ctx->comm) nccl().CommDestroy(ctx->comm);
     if (ctx->ev_ready) cudaEventDestroy(ctx->ev_ready);
     if (ctx->ev_halo) cudaEventDestroy(ctx->ev_halo);
-    if (ctx->halo_flag) cudaFree(ctx->halo_flag);
+    for (auto& kv : ctx->fields) { if (kv.second.lo) cudaIpcCloseMemHandle(kv.second.lo); if (kv.second.hi) cudaIpcCloseMemHandle(kv.second.hi); }
+    if (ctx->lo_flags) cudaIpcCloseMemHandle(ctx->lo_flags);
+    if (ctx->hi_flags) cudaIpcCloseMemHandle(ctx->hi_flags);
+    if (ctx->flags) cudaFree(ctx->flags);
+    if (ctx->xbuf) cudaFree(ctx->xbuf);
     delete ctx;
     return DEO_OK;
 }

@@ -400,11 +400,19 @@ int32_t launch_star(const deo_plan* plan, void* du, const void* u, long long z0,
 // Slab plans: ONE launch over all own planes; the CTAs of the first / last march-axis chunk (scheduled last) wait in the
 // kernel until *halo_flag >= expect, which the communication stream publishes after the neighbour exchange has landed.
 // Returns DEO_ERR_UNSUPPORTED when the slab is too thin to chunk (the caller then uses the three-launch schedule).
+StarLimits star_limits(const deo_plan* plan) {
+    StarLimits L;
+    if (!plan->star) return L;
+    const StarConfig& C = *static_cast<const StarConfig*>(plan->star.get());
+    L.fusable = C.mid && C.zchunk_max > 0;
+    L.min_fused_planes = 3LL * C.zchunk_max + 4 * C.R + 4;                 // at least 3 chunks whatever the chunk search picks (it only shortens chunks)
+    return L;
+}
+
 int32_t launch_star_fused(const deo_plan* plan, void* du, const void* u, long long cnt, cudaStream_t s, const int* halo_flag, int expect, int sides) {
     StarConfig& C = *static_cast<StarConfig*>(plan->star.get());
-    if (!C.mid) return DEO_ERR_UNSUPPORTED;
-    const long long zmax = C.zchunk_max > 0 ? C.zchunk_max : cnt;
-    if (cnt < 3 * zmax + 4 * C.R + 4) return DEO_ERR_UNSUPPORTED;          // at least 3 chunks whatever the chunk search picks
+    const StarLimits lim = star_limits(plan);
+    if (!lim.fusable || cnt < lim.min_fused_planes) return DEO_ERR_UNSUPPORTED;
     C.halo_flag = halo_flag; C.halo_expect = expect; C.halo_sides = sides;
     const int32_t rc = launch_star(plan, du, u, 0, cnt, s, false);
     C.halo_flag = nullptr;

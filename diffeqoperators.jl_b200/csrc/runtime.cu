@@ -140,6 +140,7 @@ int32_t deo_buffer_free(deo_buffer* buf) {
     if (!buf) return DEO_OK;
     if (buf->owned && buf->ptr) {
         cudaStreamSynchronize(rt().stream);
+        deo::dist_forget_buffer(buf->ptr);
         cudaFree(buf->ptr);
     }
     delete buf;
