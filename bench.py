@@ -293,6 +293,7 @@ def main():
 
     dist = None
     if N > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # keep stdout to the one JSON line if NCCL_DEBUG is set
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
