@@ -167,3 +167,49 @@ def test_julia_cumsum_is_cumsum_to_rounding():
         v = np.random.default_rng(0).random(n)
         assert np.allclose(O.julia_cumsum(v), np.cumsum(v), rtol=1e-13)
     assert np.array_equal(O.julia_cumsum(np.array([1.0, 2.0, 3.0])), [1.0, 3.0, 6.0])
+
+
+def test_periodic_second_order_value_check():
+    """test/DerivativeOperators/2nd_order_check.jl:3-38: L2*Q*u0 against the explicit periodic tridiagonal matrix, and
+    L1*Q*(L1*Q*u0) against the explicit wide second-difference matrix (PeriodicBC, bc_operators.jl:17-19,:192)."""
+    from oracle import oracle as O
+    order, h = 2, 0.025 * np.pi
+    N = int(2 * (np.pi / h))
+    x = -np.pi + h * np.arange(N)
+    L1 = O.CenteredDifference(1, order, h, N)
+    L2 = O.CenteredDifference(2, order, h, N)
+    Q = O.PeriodicBC(np.float64)
+    u0 = np.cos(x)
+    M = (np.diag(-2.0 * np.ones(N)) + np.diag(np.ones(N - 1), 1) + np.diag(np.ones(N - 1), -1))
+    M[-1, 0] = 1.0
+    M[0, -1] = 1.0
+    M /= h ** 2
+    np.testing.assert_allclose(O.apply_axis(L2, u0, Q), M @ u0, rtol=1e-9, atol=1e-9)
+    A = np.zeros((N, N))
+    for i in range(N):
+        A[i, i] = -0.5
+        for j in (i - 2, i + 2):
+            A[i, j % N] = 0.25
+    A /= h ** 2
+    np.testing.assert_allclose(O.apply_axis(L1, O.apply_axis(L1, u0, Q), Q), A @ u0, rtol=1e-9, atol=1e-9)
+
+
+def test_composite_equals_sum_of_axis_applications():
+    """test/DerivativeOperators/2D_3D_fast_multiplication.jl (e.g. :24, :73, :159-161, :667-669): a summed composite
+    applied to an array equals the sum of the per-axis applications; `overwrite=false` accumulates (convolutions.jl:49)."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(3)
+    shape = (13, 11, 12)
+    u = np.asfortranarray(rng.uniform(-1, 1, shape))
+    ops = [O.CenteredDifference(2, 4, 0.1 * (a + 1), shape[a], axis=a + 1) for a in range(3)] + \
+          [O.UpwindDifference(1, 2, 0.05, shape[1], np.sin(np.arange(shape[1])), axis=2)]
+    bcs = {a + 1: O.RobinBC((1.0, 2.0, 3.0), (0.0, -1.0, 2.0), 0.1 * (a + 1), 2) for a in range(3)}
+    total = O.apply_sum(ops, u, bcs)
+    parts = [O.apply_axis(op, u, bcs[op.axis]) for op in ops]
+    acc = parts[0]
+    for p in parts[1:]:
+        acc = acc + p
+    np.testing.assert_array_equal(total, acc)
+    out = parts[0].copy(order="F")
+    O.apply_axis(ops[1], u, bcs[2], out=out, overwrite=False)
+    np.testing.assert_array_equal(out, parts[0] + parts[1])
