@@ -109,3 +109,54 @@ def test_constructor_error_behaviour_matches_the_reference():
     A = D.CenteredDifference[1](2, 2, 0.1, 16)
     with pytest.raises(Exception):
         D.build_plans(A, (16, 8), (16, 8), np.float64)   # derivative_operator_functions.jl:40: padded dim or BC required
+
+
+def test_header_is_valid_c_and_links_from_plain_c(tmp_path):
+    """include/deo_b200.h consumed by a C11 translation unit (gcc, no C++), linked against the shipped library."""
+    import shutil
+    import subprocess
+    import deo_b200 as D
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "abi_driver")
+    libdir = os.path.dirname(D.LIB_PATH)
+    subprocess.check_call([gcc, "-std=c11", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "abi_driver.c"), "-o", exe, "-L", libdir, "-l:libdeo_b200.so",
+                           f"-Wl,-rpath,{libdir}"])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout + r.stderr
+
+
+def _struct_fields(text, name, lang):
+    """Field names of struct `name` in the C header / the Julia glue, in declaration order."""
+    if lang == "c":
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), text, flags=re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for part in decl.split(","):
+                m = re.search(r"\*?\s*([A-Za-z_][A-Za-z0-9_]*)\s*(\[[^\]]*\])?\s*$", part.strip())
+                names.append(m.group(1))
+        return names
+    body = re.search(r"struct %s\n(.*?)\nend" % name, text, flags=re.S).group(1)
+    return [m.group(1) for m in re.finditer(r"([A-Za-z_][A-Za-z0-9_]*)::", body)]
+
+
+def test_julia_glue_mirrors_the_header_field_for_field():
+    """The Julia binding cannot be executed here, so its struct images are checked statically against the header and
+    the ctypes binding (same names, same order), and every ccall names an exported symbol."""
+    from deo_b200 import _lib
+    hdr = open(HEADER).read()
+    jl = open(os.path.join(ROOT, "diffeqoperators.jl_b200", "julia", "DiffEqOperatorsB200.jl")).read()
+    for cname, jname, ctype in [("deo_op_desc", "OpDesc", _lib.OpDesc), ("deo_bc_desc", "BcDesc", _lib.BcDesc), ("deo_plan_desc", "PlanDesc", _lib.PlanDesc)]:
+        c_fields = _struct_fields(hdr, cname, "c")
+        j_fields = _struct_fields(jl, jname, "jl")
+        py_fields = [f[0] for f in ctype._fields_]
+        assert c_fields == py_fields, (cname, c_fields, py_fields)
+        assert c_fields == j_fields, (cname, c_fields, j_fields)
+    called = set(re.findall(r"ccall\(\(:(deo_[a-z0-9_]+), libdeo\)", jl))
+    assert called and called <= set(_declared_functions()), called - set(_declared_functions())
