@@ -388,7 +388,9 @@ def main():
     alg_bytes = 2.0 * es * local_pts
     achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(name), "peak_source": peak_src, "kernel": kernel_name,
+                "traffic": (ncu_traffic(name) * local_pts / float(np.prod(WORKLOADS[name][0])) if ncu_traffic(name) else None),
+                "traffic_note": "dram bytes per launch from the committed single-GPU ncu capture (profiles/traffic.json), scaled to this rank's points",
+                "peak_source": peak_src, "kernel": kernel_name,
                 "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_kernel,
                 "frac_of_8TBs_nominal": achieved / 8000.0}
 

@@ -257,8 +257,9 @@ def _get_plans(A, out_shape, in_shape, dtype, accumulate, flags, Q_override=None
     cache = A.__dict__.setdefault(_PLAN_CACHE_ATTR, {})
     key = (tuple(out_shape), tuple(in_shape), np.dtype(dtype).str, bool(accumulate), flags, _coeff_versions(A), id(Q_override))
     if key not in cache:
-        cache[key] = build_plans(A, out_shape, in_shape, dtype, accumulate, flags, Q_override)
-    return cache[key]
+        # the entry keeps Q_override alive, so its id() cannot be recycled for another boundary operator while cached
+        cache[key] = (build_plans(A, out_shape, in_shape, dtype, accumulate, flags, Q_override), Q_override)
+    return cache[key][0]
 
 
 def _unwrap(u):
