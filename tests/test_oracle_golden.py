@@ -213,3 +213,31 @@ def test_composite_equals_sum_of_axis_applications():
     out = parts[0].copy(order="F")
     O.apply_axis(ops[1], u, bcs[2], out=out, overwrite=False)
     np.testing.assert_array_equal(out, parts[0] + parts[1])
+
+
+def _matrix_by_multiplication(op, n):
+    """Array(L) by applying the 1-D operator to unit vectors of the padded space (concretization.jl:8-48 equivalent)."""
+    from oracle import oracle as O
+    M = np.zeros((n, n + 2))
+    for k in range(n + 2):
+        e = np.zeros(n + 2)
+        e[k] = 1.0
+        M[:, k] = O.apply_axis(op, e)
+    return M
+
+
+def test_nd_nonsymmetric_stencils_and_coefficients_equal_matrix_times_pencils():
+    """test/DerivativeOperators/differentiation_dimension.jl:209-302 (non-symmetric interior stencil (3,4)) and :304-370
+    (operators with coefficients): mul! along axis N of a 2-D / 3-D array equals Array(L) applied to every pencil."""
+    from oracle import oracle as O
+    n = 30
+    for coeff in (1, 2.5, np.linspace(0.5, 1.5, n)):
+        for shape, axis in [((32, 32), 1), ((32, 32), 2), ((32, 32, 32), 1), ((32, 32, 32), 2), ((32, 32, 32), 3)]:
+            L = O.CenteredDifference(3, 4, 0.1, n, coeff, axis=axis)
+            A = _matrix_by_multiplication(O.CenteredDifference(3, 4, 0.1, n, coeff, axis=1), n)
+            idx = np.indices(shape)[axis - 1] + 1
+            M = np.asfortranarray(np.cos(0.1 * idx))
+            got = O.apply_axis(L, M)
+            want = np.moveaxis(np.tensordot(A, np.moveaxis(M, axis - 1, 0), axes=(1, 0)), 0, axis - 1)
+            assert got.shape == tuple(s - 2 if d == axis - 1 else s for d, s in enumerate(shape))
+            np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-9)
