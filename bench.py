@@ -29,71 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-WORKLOADS = {
-    # name: (shape, approximation order, dtype, description)
-    "C5": ((1024, 1024, 1024), 4, np.float64, "C5: 3-D Laplacian Dxx+Dyy+Dzz CenteredDifference(2,4) + RobinBC, 1024^3 Float64, slabs along dim 3"),
-    "C3": ((512, 512, 512), 6, np.float64, "C3: 3-D Laplacian (2,6) + Neumann MultiDimBC, 512^3 Float64"),
-    "C3f32": ((512, 512, 512), 6, np.float32, "C3: 3-D Laplacian (2,6) + Neumann MultiDimBC, 512^3 Float32"),
-    "C2": ((8192, 8192), 4, np.float64, "C2: 2-D Laplacian Dxx+Dyy (2,4) + RobinBC, 8192^2 Float64"),
-    "C1": ((10 ** 6,), 2, np.float64, "C1: 1-D heat-equation Laplacian CenteredDifference(2,2)*Dirichlet0BC, N=1e6 Float64"),
-    "C4": ((512, 512, 512), 4, np.float64, "C4: non-uniform 512^3 Float64, sum over axes of CenteredDifference(2,4) + CenteredDifference(1,4) + "
-           "UpwindDifference(1,2) with a mixed-sign coefficient vector, RobinBC from the same spacings (9 operators, one pass)"),
-}
-ROBIN_L, ROBIN_R = (1.0, 0.5, 0.25), (1.0, -0.5, 0.75)
-
-
-def c4_inputs(shape, dtype):
-    """Spacing vectors and coefficient vectors of BASELINE config 4."""
-    hs = [1.0 / (s + 1) for s in shape]
-    dxs = [(h * (1 + 0.3 * np.sin(2 * np.pi * np.arange(1, s + 2) / (s + 1)))).astype(dtype) for s, h in zip(shape, hs)]
-    cs = [np.sin(6 * np.pi * np.arange(1, s + 1) / s).astype(dtype) for s in shape]
-    return dxs, cs
-
-
-def build_operator(D, name, shape, dtype):
-    """The product-side operator A*Q of a workload (host mirror of the reference constructors)."""
-    _, a, _, _ = WORKLOADS[name]
-    nd = len(shape)
-    h = tuple(1.0 / (s + 1) for s in shape)
-    if name == "C4":
-        dxs, cs = c4_inputs(shape, dtype)
-        ops = [D.CenteredDifference[ax](2, 4, dxs[ax - 1], shape[ax - 1], dtype=dtype) for ax in range(1, nd + 1)] + \
-              [D.CenteredDifference[ax](1, 4, dxs[ax - 1], shape[ax - 1], dtype=dtype) for ax in range(1, nd + 1)] + \
-              [D.UpwindDifference[ax](1, 2, dxs[ax - 1], shape[ax - 1], cs[ax - 1], dtype=dtype) for ax in range(1, nd + 1)]
-        A = ops[0]
-        for o in ops[1:]:
-            A = A + o
-        return A * D.compose(*D.RobinBC(ROBIN_L, ROBIN_R, dxs, 1, shape, dtype=dtype))
-    if nd == 1:
-        return D.CenteredDifference(2, a, h[0], shape[0], dtype=dtype) * D.Dirichlet0BC(dtype)
-    A = D.CenteredDifference[1](2, a, h[0], shape[0], dtype=dtype)
-    for ax in range(2, nd + 1):
-        A = A + D.CenteredDifference[ax](2, a, h[ax - 1], shape[ax - 1], dtype=dtype)
-    if name.startswith("C3"):
-        Q = D.compose(*D.Neumann0BC(dtype, h, 1, shape))
-    else:
-        Q = D.compose(*D.RobinBC(ROBIN_L, ROBIN_R, h, 1, shape, dtype=dtype))
-    return A * Q
-
-
-def build_oracle(O, name, shape, dtype):
-    _, a, _, _ = WORKLOADS[name]
-    nd = len(shape)
-    h = tuple(1.0 / (s + 1) for s in shape)
-    if name == "C4":
-        dxs, cs = c4_inputs(shape, dtype)
-        ops = [O.CenteredDifference(2, 4, dxs[ax], shape[ax], axis=ax + 1, dtype=dtype) for ax in range(nd)] + \
-              [O.CenteredDifference(1, 4, dxs[ax], shape[ax], axis=ax + 1, dtype=dtype) for ax in range(nd)] + \
-              [O.UpwindDifference(1, 2, dxs[ax], shape[ax], cs[ax], axis=ax + 1, dtype=dtype) for ax in range(nd)]
-        return ops, {ax + 1: O.RobinBC(ROBIN_L, ROBIN_R, dxs[ax], 1, dtype) for ax in range(nd)}
-    ops = [O.CenteredDifference(2, a, h[ax], shape[ax], axis=ax + 1, dtype=dtype) for ax in range(nd)]
-    if nd == 1:
-        bcs = {1: O.Dirichlet0BC(dtype)}
-    elif name.startswith("C3"):
-        bcs = {ax + 1: O.Neumann0BC(h[ax], 1, dtype) for ax in range(nd)}
-    else:
-        bcs = {ax + 1: O.RobinBC(ROBIN_L, ROBIN_R, h[ax], 1, dtype) for ax in range(nd)}
-    return ops, bcs
+from tools.workloads import (WORKLOADS, ROBIN_L, ROBIN_R, build_operator, build_oracle, check_rows, field_planes)  # noqa: E402
 
 
 def cpu_sample_shape(shape):
@@ -261,6 +197,103 @@ def run_reference(args):
     return 0
 
 
+def pinned_array(L, shape_, dt):
+    """Column-major numpy array over pinned host memory (deo_host_alloc); pageable fallback."""
+    import ctypes as C
+    from deo_b200 import _lib
+    nbytes = int(np.prod(shape_)) * np.dtype(dt).itemsize
+    p = C.c_void_p()
+    try:
+        _lib.check(L.deo_host_alloc(nbytes, C.byref(p)))
+        buf = (C.c_char * nbytes).from_address(p.value)
+        return np.frombuffer(buf, dtype=dt).reshape(shape_, order="F"), p
+    except Exception:
+        return np.empty(shape_, dtype=dt, order="F"), None
+
+
+def parity_of_rows(name, gshape, dtype, du_local, start, count, nthreads, planes=8):
+    """Checker leg (outside every timed region): the first / middle / last `planes` rows of this rank's slab of the TIMED
+    result against the CPU oracle on the same reproducible field -> (max abs err, max |oracle|, boundary-only max abs err,
+    rows checked)."""
+    from oracle import oracle as O
+    u_of = lambda a, b: field_planes(gshape, dtype, a, b)
+    if len(gshape) == 1:
+        e, r, b = check_rows(O, name, gshape, dtype, du_local, 0, gshape[0], u_of, nthreads)
+        return e, r, b, int(gshape[0])
+    planes = min(planes, count)
+    starts = sorted({0, max((count - planes) // 2, 0), count - planes})
+    err = ref = berr = 0.0
+    for s0 in starts:
+        e, r, b = check_rows(O, name, gshape, dtype, du_local[..., s0:s0 + planes], start + s0, start + s0 + planes, u_of, nthreads)
+        err, ref, berr = max(err, e), max(ref, r), max(berr, b)
+    return err, ref, berr, planes * len(starts)
+
+
+def roofline_dict(name, kernel_name, alg_bytes, ms_kernel, local_frac=1.0):
+    peak, peak_src = measured_peak()
+    achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
+    tr = ncu_traffic(name)
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": (tr * local_frac if tr else None),
+            "traffic_note": "dram bytes per launch from the committed single-GPU ncu capture (profiles/traffic.json), scaled to this rank's points",
+            "peak_source": peak_src, "kernel": kernel_name,
+            "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_kernel,
+            "frac_of_8TBs_nominal": achieved / 8000.0}
+
+
+def table_bytes(G, dtype):
+    """Coefficient traffic counted once per application: per-row weight tables and coefficient vectors."""
+    from deo_b200.apply import _terms
+    es = np.dtype(dtype).itemsize
+    b = 0
+    for Lop, _ in _terms(G):
+        if Lop.nonuniform:
+            b += (np.asarray(Lop.stencil_coefs).size + np.asarray(Lop.low_boundary_coefs).size + np.asarray(Lop.high_boundary_coefs).size) * es
+        if np.ptp(np.asarray(Lop.coefficients)) != 0:
+            b += Lop.len * es
+    return b
+
+
+def run_single_config(D, L, name, steps, warmup, device, check=True):
+    """One BASELINE configuration on one GPU, kernel-only: K graph-replayed applications between CUDA events on the
+    library stream, inputs resident; then the timed result is checked against the oracle (checker leg, untimed)."""
+    import ctypes as C
+    from deo_b200 import _lib
+    shape, _, dtype, desc = WORKLOADS[name]
+    es = np.dtype(dtype).itemsize
+    G = build_operator(D, name, shape, dtype)
+    plan = D.build_plans(G, shape, shape, dtype)[0][0]
+    kernel_name, _ = plan.info
+    u_host = field_planes(shape, dtype, 0, shape[-1])
+    u = D.DeviceArray.from_host(u_host)
+    del u_host
+    du = D.DeviceArray(shape, dtype)
+    reps = max(steps, 1000) if name == "C1" else steps      # C1: >= 1000 back-to-back applies from one graph (SURVEY 8d)
+    for _ in range(max(warmup, 3)):
+        plan.apply(du, u)
+    D.sync()
+    plan.time(du, u, reps)                                   # builds and warms the graph
+    with ClockSampler(device) as clk:
+        ms = plan.time(du, u, reps)
+        if name == "C1":
+            for _ in range(20):                              # a 3 ms region is too short for the 3 ms NVML poll: repeat it
+                ms = min(ms, plan.time(du, u, reps))
+    pts = float(np.prod(shape))
+    alg = 2.0 * es * pts + table_bytes(G, dtype)
+    out = {"config": name, "workload": desc, "shape": list(shape), "dtype": "f64" if es == 8 else "f32", "kernel": kernel_name,
+           "steps": reps, "ms_per_step": ms, "value": pts / (ms * 1e-3) / 1e9, "unit": "Gpoints/s",
+           "roofline": roofline_dict(name, kernel_name, alg, ms), "clocks": clk.summary(),
+           "l2": "working set (16 MB) is L2-resident: the HBM fraction is nominal" if name == "C1" else "field >= 1 GB, far larger than the 126 MB L2"}
+    if name == "C1":
+        out["single_launch_ms"] = min(plan.time(du, u, 1) for _ in range(20))
+    if check:
+        got = du.to_host()
+        e, r, b, rows = parity_of_rows(name, shape, dtype, got, 0, shape[-1], os.cpu_count() or 1)
+        out["parity"] = {"max_rel_err": e / r, "boundary_max_rel_err": b / r, "rows_checked": rows,
+                         "gate": 1e-13 if es == 8 else 1e-5, "against": "CPU oracle (oracle/), same seeded field"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -272,6 +305,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--nz", type=int, default=0, help="override the last extent of the workload (experiments; not a BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config array (C1..C4) of the single-GPU line")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed result")
     ap.add_argument("--force-generic", action="store_true", help="run the per-point kernel instead of the tiled one (A/B)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -327,34 +362,33 @@ def main():
     total_pts = float(np.prod(gshape))
 
     from deo_b200.dist import SlabContext, SlabPlan
-    rng = np.random.default_rng(1234 + rank)
     if N > 1:
         ctx = SlabContext.from_torch_distributed(device=local_rank)
         plan = SlabPlan(G, gshape, dtype, ctx=ctx, flags=flags)
         in_shape, out_shape = plan.local_in_shape, plan.local_out_shape
+        start, count, halo = plan.start, plan.count, plan.halo
     else:
         plan = D.build_plans(G, gshape, gshape, dtype, flags=flags)[0][0]
         in_shape, out_shape = gshape, gshape
+        start, count, halo = 0, gshape[-1], 0
     kernel_name, launches_per_apply = plan.info
     local_pts = float(np.prod(out_shape))
 
-    # synthetic field: iid Uniform(-1,1), generated on the host in pinned memory (also the e2e source buffer)
-    def pinned(shape_, dt):
-        nbytes = int(np.prod(shape_)) * np.dtype(dt).itemsize
-        p = C.c_void_p()
-        try:
-            _lib.check(L.deo_host_alloc(nbytes, C.byref(p)))
-            buf = (C.c_char * nbytes).from_address(p.value)
-            return np.frombuffer(buf, dtype=dt).reshape(shape_, order="F"), p
-        except Exception:
-            return np.empty(shape_, dtype=dt, order="F"), None
-
-    u_host, u_pin = pinned(in_shape, dtype)
-    du_host, du_pin = pinned(out_shape, dtype)
-    flat = u_host.reshape(-1, order="F")
-    chunk = 1 << 24
-    for i in range(0, flat.size, chunk):          # chunked fill keeps the temporary small
-        flat[i:i + chunk] = rng.uniform(-1, 1, min(chunk, flat.size - i)).astype(dtype)
+    # synthetic field: iid Uniform(-1,1), reproducible plane by plane, generated on the host in pinned memory (also the
+    # e2e source buffer).  A rank's buffer is [halo | own planes | halo]; its halo planes hold the neighbours' values
+    # (the exchange rewrites them with the same numbers), zeros outside the physical faces.
+    u_host, u_pin = pinned_array(L, in_shape, dtype)
+    du_host, du_pin = pinned_array(L, out_shape, dtype)
+    if len(gshape) == 1:
+        u_host[...] = field_planes(gshape, dtype, 0, gshape[0])
+    else:
+        n_last = gshape[-1]
+        u_host[...] = 0
+        g0, g1 = max(start - halo, 0), min(start + count + halo, n_last)
+        blk = 64
+        for a in range(g0, g1, blk):                 # chunked fill keeps the temporary small
+            b = min(a + blk, g1)
+            u_host[..., a - (start - halo):b - (start - halo)] = field_planes(gshape, dtype, a, b)
     u = D.DeviceArray(in_shape, dtype)
     du = D.DeviceArray(out_shape, dtype)
     _lib.check(L.deo_buffer_upload(u._h, u_host.ctypes.data_as(C.c_void_p), u.nbytes))
@@ -371,10 +405,9 @@ def main():
     with ClockSampler(local_rank) as clk:
         barrier()
         D.sync()
-        if N == 1:
-            ms_step = plan.time(du, u, args.steps)            # CUDA events on the library stream around K graph-replayed applies
-        else:
-            ms_step = plan.time(du, u, args.steps)            # events around K {exchange || interior, boundary} applies
+        # N == 1: CUDA events on the library stream around K graph-replayed applies;
+        # N > 1 : events around K applies, each = {copy-engine halo pushes || ONE fused stencil launch}
+        ms_step = plan.time(du, u, args.steps)
         D.sync()
         barrier()
     ms_step = max_over_ranks(ms_step)
@@ -382,17 +415,23 @@ def main():
     clocks = clk.summary()
     value = total_pts / (ms_step * 1e-3) / 1e9
 
-    # ---- kernel-only roofline (the dominant kernel timed alone, same events) --------------------------------
-    peak, peak_src = measured_peak()
-    ms_kernel = ms_step if N == 1 else max_over_ranks(plan.time(du, u, max(3, args.steps // 2)))
-    alg_bytes = 2.0 * es * local_pts
-    achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": (ncu_traffic(name) * local_pts / float(np.prod(WORKLOADS[name][0])) if ncu_traffic(name) else None),
-                "traffic_note": "dram bytes per launch from the committed single-GPU ncu capture (profiles/traffic.json), scaled to this rank's points",
-                "peak_source": peak_src, "kernel": kernel_name,
-                "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_kernel,
-                "frac_of_8TBs_nominal": achieved / 8000.0}
+    # ---- roofline of the dominant kernel: one launch per step (N > 1: the fused slab launch, which includes its
+    # in-kernel wait for the halo planes, so ms_per_launch == ms_per_step there) ---------------------------------
+    alg_bytes = 2.0 * es * local_pts + table_bytes(G, dtype)
+    roofline = roofline_dict(name, kernel_name, alg_bytes, ms_step, local_pts / float(np.prod(WORKLOADS[name][0])))
+    if N > 1:
+        roofline["note"] = "per rank: this rank's algorithmic bytes over the step time (halo exchange and in-kernel halo wait included)"
+
+    # ---- parity of the TIMED result against the oracle (untimed checker leg) -----------------------------------
+    parity = None
+    if not args.no_parity and not args.force_generic:
+        _lib.check(L.deo_buffer_download(du_host.ctypes.data_as(C.c_void_p), du._h, du.nbytes))
+        nthreads = max(1, (os.cpu_count() or 1) // N)
+        e, r, b, rows = parity_of_rows(name, gshape, dtype, du_host, start, count, nthreads)
+        rel, brel = max_over_ranks(e / r), max_over_ranks(b / r)
+        parity = {"max_rel_err": rel, "boundary_max_rel_err": brel, "rows_checked_per_rank": rows, "ranks": N,
+                  "gate": 1e-13 if es == 8 else 1e-5, "pass": bool(rel <= (1e-13 if es == 8 else 1e-5)),
+                  "against": "CPU oracle (oracle/) on the same reproducible field: first / middle / last planes of every rank's slab"}
 
     # ---- end to end through the public host-buffer API: H2D(u) + apply + D2H(du) every step ------------------
     e2e_steps = max(1, args.e2e_steps)
@@ -403,9 +442,7 @@ def main():
         if N == 1:
             D.mul_(du_host, G, u_host, flags=flags)                 # deo_plan_apply_host: upload, fused kernel, download
         else:
-            _lib.check(L.deo_buffer_upload(u._h, u_host.ctypes.data_as(C.c_void_p), h2d))
-            plan.apply(du, u)
-            _lib.check(L.deo_buffer_download(du_host.ctypes.data_as(C.c_void_p), du._h, d2h))
+            plan.apply_host(du_host, u_host)                        # deo_dist_plan_apply_host: the same pipeline on a slab
     e2e_step()
     barrier()
     t0 = time.perf_counter()
@@ -428,6 +465,17 @@ def main():
             gN, _, _ = time_oracle(name, dtype, 2, 0, nthreads)
             cpu["all_threads"] = {"value": gN, "cores": nthreads}
 
+    # ---- the other BASELINE configurations, kernel-only with their own oracle check (N == 1 only) -------------------
+    configs = None
+    if N == 1 and not args.no_configs and name == "C5" and args.nz == 0 and not args.force_generic:
+        del u, du
+        configs = []
+        for cname in ("C1", "C2", "C3", "C3f32", "C4"):
+            try:
+                configs.append(run_single_config(D, L, cname, args.steps, args.warmup, local_rank, check=not args.no_parity))
+            except Exception as exc:          # a failing side config must not hide the headline line
+                configs.append({"config": cname, "error": repr(exc)})
+
     if rank == 0:
         line = {
             "metric": "stencil Gpoints/s (mul!, Float64)" if dtype == np.float64 else "stencil Gpoints/s (mul!, Float32)",
@@ -437,11 +485,15 @@ def main():
             "config": {"workload": desc if args.scaling == "strong" or N == 1 else desc + f" (weak: {'x'.join(map(str, gshape))} global)",
                        "global_shape": list(gshape), "parallelism": f"slab{N}" if N > 1 else "single", "kernel": kernel_name,
                        "l2": "input (>= 8 GB) far exceeds the 126 MB L2; no flush needed" if total_pts * es > 1e9 else "working set may be L2-resident",
-                       "values": "iid Uniform(-1,1), seeded"},
+                       "values": "iid Uniform(-1,1), seeded per plane"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         }
+        if parity is not None:
+            line["parity"] = parity
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if configs is not None:
+            line["configs"] = configs
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

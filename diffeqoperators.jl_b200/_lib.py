@@ -78,6 +78,7 @@ EXPORTS = {
     "deo_dist_plan_create": [C.c_void_p, C.POINTER(PlanDesc), C.POINTER(C.c_void_p)],
     "deo_dist_plan_halo": [C.c_void_p, C.POINTER(C.c_int32)],
     "deo_dist_plan_apply": [C.c_void_p, C.c_void_p, C.c_void_p],
+    "deo_dist_plan_apply_host": [C.c_void_p, C.c_void_p, C.c_void_p],
     "deo_dist_plan_time": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_float)],
     "deo_dist_plan_create_local": [C.POINTER(PlanDesc), C.c_int32, C.c_int32, C.POINTER(C.c_void_p)],
 }

@@ -47,6 +47,7 @@ struct NcclApi {
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     bool ok = false;
 };
@@ -68,8 +69,9 @@ NcclApi& nccl() {
     api.Recv = (decltype(api.Recv))sym("ncclRecv");
     api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
     api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+    api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
     api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
-    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Send && api.Recv && api.GroupStart && api.GroupEnd;
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Send && api.Recv && api.GroupStart && api.GroupEnd && api.AllReduce;
     return api;
 }
 
@@ -95,7 +97,7 @@ enum { F_HALO_FROM_LOW = 0,   // the low neighbour's planes for application i ha
        F_ACKWORD = 5,
        F_COUNT = 16 };
 
-struct PeerField { void* lo = nullptr; void* hi = nullptr; };
+struct PeerField { void* lo = nullptr; void* hi = nullptr; bool ok = false; };
 
 struct deo_dist {
     ncclComm_t comm = nullptr;
@@ -106,6 +108,7 @@ struct deo_dist {
     int* flags = nullptr;                  // F_COUNT ints
     int *lo_flags = nullptr, *hi_flags = nullptr;   // the neighbours' flag arrays, mapped
     unsigned char* xbuf = nullptr;         // 3 x 64 bytes device staging for the handle exchange
+    int* abuf = nullptr;                   // 2 ints: agreement all-reduce
     std::map<void*, PeerField> fields;     // my field buffer -> the neighbours' mappings of theirs
     int step = 0;
 };
@@ -137,6 +140,21 @@ PFN_streamValue32 stream_op(const char* name) {
 PFN_streamValue32 wait_value32() { static PFN_streamValue32 f = stream_op("cuStreamWaitValue32"); return f; }
 PFN_streamValue32 write_value32() { static PFN_streamValue32 f = stream_op("cuStreamWriteValue32"); return f; }
 
+// Collective over ALL ranks: true only where `mine` is true on every rank.  Every decision that selects a schedule
+// (peer-to-peer pushes + flags vs. NCCL send/recv) goes through this, so two neighbours can never run different
+// protocols against each other.
+int32_t agree(deo_dist* ctx, bool mine, bool* all) {
+    NcclApi& N = nccl();
+    cudaStream_t cs = rt().comm_stream;
+    int v = mine ? 1 : 0, out = 0;
+    DEO_CUDA(cudaMemcpyAsync(ctx->abuf, &v, sizeof(int), cudaMemcpyHostToDevice, cs));
+    DEO_NCCL(N.AllReduce(ctx->abuf, ctx->abuf + 1, 1, ncclInt32, 3 /* ncclMin */, ctx->comm, cs));
+    DEO_CUDA(cudaMemcpyAsync(&out, ctx->abuf + 1, sizeof(int), cudaMemcpyDeviceToHost, cs));
+    DEO_CUDA(cudaStreamSynchronize(cs));
+    *all = out == 1;
+    return DEO_OK;
+}
+
 // Neighbours swap one 64-byte CUDA IPC handle each way (through NCCL, the only channel the library has); collective
 // over the slab neighbours, synchronous.  lo/hi are left untouched where there is no neighbour.
 int32_t swap_handles(deo_dist* ctx, const cudaIpcMemHandle_t& mine, cudaIpcMemHandle_t* lo, cudaIpcMemHandle_t* hi) {
@@ -157,21 +175,34 @@ int32_t swap_handles(deo_dist* ctx, const cudaIpcMemHandle_t& mine, cudaIpcMemHa
     return DEO_OK;
 }
 
-// Maps the neighbours' copies of one exported allocation.  Collective over the slab neighbours.
-int32_t map_neighbours(deo_dist* ctx, void* mine, void** lo, void** hi) {
+// Maps the neighbours' copies of one exported allocation.  Collective over ALL ranks: the handle swap always takes
+// place (a rank whose export failed sends zeros) and the outcome is agreed on, so *mapped is the same everywhere.
+// A non-zero return is a broken communicator (fatal), not a failed mapping.
+int32_t map_neighbours(deo_dist* ctx, void* mine, void** lo, void** hi, bool* mapped) {
     cudaIpcMemHandle_t hm, hl, hh;
-    DEO_CUDA(cudaIpcGetMemHandle(&hm, mine));
+    bool good = mine != nullptr && cudaIpcGetMemHandle(&hm, mine) == cudaSuccess;
+    if (!good) { memset(&hm, 0, sizeof hm); cudaGetLastError(); }
     int32_t rc = swap_handles(ctx, hm, &hl, &hh);
     if (rc) return rc;
     *lo = *hi = nullptr;
-    if (ctx->rank > 0) DEO_CUDA(cudaIpcOpenMemHandle(lo, hl, cudaIpcMemLazyEnablePeerAccess));
-    if (ctx->rank + 1 < ctx->nranks) DEO_CUDA(cudaIpcOpenMemHandle(hi, hh, cudaIpcMemLazyEnablePeerAccess));
+    bool peers = false;
+    rc = agree(ctx, good, &peers);            // opening a zeroed handle is pointless: first agree that every export worked
+    if (rc) return rc;
+    if (peers) {
+        if (ctx->rank > 0 && cudaIpcOpenMemHandle(lo, hl, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { good = false; *lo = nullptr; }
+        if (ctx->rank + 1 < ctx->nranks && cudaIpcOpenMemHandle(hi, hh, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { good = false; *hi = nullptr; }
+        if (!good) cudaGetLastError();
+        rc = agree(ctx, good, &peers);
+        if (rc) return rc;
+    }
+    if (!peers) {
+        if (*lo) cudaIpcCloseMemHandle(*lo);
+        if (*hi) cudaIpcCloseMemHandle(*hi);
+        *lo = *hi = nullptr;
+    }
+    *mapped = peers;
     return DEO_OK;
 }
-
-}  // namespace
-
-namespace {
 
 // Reach of the operators acting on `axis`, in planes, below and above the output row.
 int axis_reach(const deo_plan* plan, int axis) {
@@ -228,6 +259,79 @@ int32_t make_slab_plan(const deo_plan_desc* desc, int rank, int nranks, deo_dist
     return DEO_OK;
 }
 
+#define DEO_DRV(call, what)                                                                  \
+    do {                                                                                     \
+        if ((call) != CUDA_SUCCESS) { set_error("%s failed", what); return DEO_ERR_CUDA; }  \
+    } while (0)
+
+// The neighbours' mappings of field buffer `ptr` (collective registration on first use).  pf->ok is the same on every
+// rank: false means "use the NCCL schedule for this buffer".
+int32_t peer_field(deo_dist* ctx, void* ptr, const PeerField** pf) {
+    auto it = ctx->fields.find(ptr);
+    if (it == ctx->fields.end()) {
+        DEO_CUDA(cudaStreamSynchronize(rt().stream));
+        PeerField f;
+        int32_t rc = map_neighbours(ctx, ptr, &f.lo, &f.hi, &f.ok);
+        if (rc) return rc;
+        it = ctx->fields.emplace(ptr, f).first;
+    }
+    *pf = &it->second;
+    return DEO_OK;
+}
+
+// Peer-to-peer halo exchange of application `step`, enqueued on the communication stream: my first / last H own planes
+// go straight into the neighbours' field buffers (mapped through CUDA IPC) over NVLink by the copy engines, each followed
+// by a 4-byte flag.  `ready_lo` / `ready_hi`: events after which my first / last H own planes are valid.  Before
+// overwriting a neighbour's halo planes the stream waits (cuStreamWaitValue32) until that neighbour has reported the
+// previous application finished.  No kernel takes part, so the exchange cannot compete with the stencil kernel for SMs.
+int32_t push_halos(deo_dist* ctx, const deo_plan* plan, const PeerField& pf, char* base, int step, cudaEvent_t ready_lo, cudaEvent_t ready_hi) {
+    Runtime& R = rt();
+    const int H = plan->halo;
+    const long long cnt = plan->slab_count;
+    const size_t plane_b = (size_t)plan->in_dim(0) * (size_t)plan->in_dim(1) * plan->elem();
+    const int lo = plan->rank - 1, hi = plan->rank + 1;
+    const bool has_lo = lo >= 0, has_hi = hi < plan->nranks;
+    CUstream cs = (CUstream)R.comm_stream;
+    DEO_DRV(write_value32()(cs, (CUdeviceptr)(ctx->flags + F_STEPWORD), (cuuint32_t)step, CU_STREAM_WRITE_VALUE_DEFAULT), "cuStreamWriteValue32");
+    if (has_lo) {
+        int64_t s_lo = 0, c_lo = 0;
+        deo_dist_slab(plan->dims[plan->slab_axis], plan->nranks, lo, &s_lo, &c_lo);
+        DEO_CUDA(cudaStreamWaitEvent(R.comm_stream, ready_lo, 0));
+        DEO_DRV(wait_value32()(cs, (CUdeviceptr)(ctx->flags + F_LOW_DONE), (cuuint32_t)(step - 1), CU_STREAM_WAIT_VALUE_GEQ), "cuStreamWaitValue32");
+        DEO_CUDA(cudaMemcpyAsync((char*)pf.lo + (size_t)(H + c_lo) * plane_b, base + (size_t)H * plane_b, (size_t)H * plane_b, cudaMemcpyDefault, R.comm_stream));
+        DEO_CUDA(cudaMemcpyAsync(ctx->lo_flags + F_HALO_FROM_HIGH, ctx->flags + F_STEPWORD, sizeof(int), cudaMemcpyDefault, R.comm_stream));
+    }
+    if (has_hi) {
+        DEO_CUDA(cudaStreamWaitEvent(R.comm_stream, ready_hi, 0));
+        DEO_DRV(wait_value32()(cs, (CUdeviceptr)(ctx->flags + F_HIGH_DONE), (cuuint32_t)(step - 1), CU_STREAM_WAIT_VALUE_GEQ), "cuStreamWaitValue32");
+        DEO_CUDA(cudaMemcpyAsync((char*)pf.hi, base + (size_t)cnt * plane_b, (size_t)H * plane_b, cudaMemcpyDefault, R.comm_stream));
+        DEO_CUDA(cudaMemcpyAsync(ctx->hi_flags + F_HALO_FROM_LOW, ctx->flags + F_STEPWORD, sizeof(int), cudaMemcpyDefault, R.comm_stream));
+    }
+    return DEO_OK;
+}
+
+// Tells the neighbours (after everything queued on stream `s`) that application `step` is finished here: they may
+// overwrite my halo planes.
+int32_t ack_done(deo_dist* ctx, const deo_plan* plan, int step, cudaStream_t s) {
+    const bool has_lo = plan->rank > 0, has_hi = plan->rank + 1 < plan->nranks;
+    DEO_DRV(write_value32()((CUstream)s, (CUdeviceptr)(ctx->flags + F_ACKWORD), (cuuint32_t)step, CU_STREAM_WRITE_VALUE_DEFAULT), "cuStreamWriteValue32");
+    if (has_lo) DEO_CUDA(cudaMemcpyAsync(ctx->lo_flags + F_HIGH_DONE, ctx->flags + F_ACKWORD, sizeof(int), cudaMemcpyDefault, s));
+    if (has_hi) DEO_CUDA(cudaMemcpyAsync(ctx->hi_flags + F_LOW_DONE, ctx->flags + F_ACKWORD, sizeof(int), cudaMemcpyDefault, s));
+    return DEO_OK;
+}
+
+// The halo planes outside a physical face are never part of a result, but the tiled kernel streams them through its
+// pipeline (multiplied by zero weights at most): keep them finite.
+int32_t clear_outer_halos(const deo_plan* plan, void* u, cudaStream_t s) {
+    const int H = plan->halo;
+    if (H <= 0) return DEO_OK;
+    const size_t plane_b = (size_t)plan->in_dim(0) * (size_t)plan->in_dim(1) * plan->elem();
+    if (plan->rank == 0) DEO_CUDA(cudaMemsetAsync(u, 0, (size_t)H * plane_b, s));
+    if (plan->rank == plan->nranks - 1)
+        DEO_CUDA(cudaMemsetAsync((char*)u + (size_t)(plan->slab_count + H) * plane_b, 0, (size_t)H * plane_b, s));
+    return DEO_OK;
+}
+
 int32_t dist_apply(deo_plan* plan, deo_buffer* du, deo_buffer* u) {
     DEO_REQUIRE(plan && du && u, "deo_dist_plan_apply: null argument");
     DEO_REQUIRE(plan->slab_axis >= 0, "deo_dist_plan_apply: not a slab plan");
@@ -238,14 +342,8 @@ int32_t dist_apply(deo_plan* plan, deo_buffer* du, deo_buffer* u) {
     const long long cnt = plan->slab_count;
     const int H = plan->halo;
     deo_dist* ctx = plan->dist;
-    // The halo planes outside a physical face are never part of a result, but the tiled kernel streams them
-    // through its pipeline (multiplied by zero weights at most): keep them finite.
-    if (H > 0) {
-        const size_t plane_b = (size_t)plan->in_dim(0) * (size_t)plan->in_dim(1) * plan->elem();
-        if (plan->rank == 0) DEO_CUDA(cudaMemsetAsync(u->ptr, 0, (size_t)H * plane_b, R.stream));
-        if (plan->rank == plan->nranks - 1)
-            DEO_CUDA(cudaMemsetAsync((char*)u->ptr + (size_t)(cnt + H) * plane_b, 0, (size_t)H * plane_b, R.stream));
-    }
+    int32_t rc = clear_outer_halos(plan, u->ptr, R.stream);
+    if (rc) return rc;
     if (!ctx || plan->nranks == 1 || H == 0) {   // local emulation or single rank: halos are the caller's business
         g_launches += 1;
         return launch_plan(plan, du->ptr, u->ptr, 0, cnt, R.stream);
@@ -258,51 +356,25 @@ int32_t dist_apply(deo_plan* plan, deo_buffer* du, deo_buffer* u) {
     const int lo = plan->rank - 1, hi = plan->rank + 1;
     const bool has_lo = lo >= 0, has_hi = hi < plan->nranks;
     // ---- fused schedule: peer-to-peer halo pushes by the copy engines + ONE kernel launch for the whole slab ----------
-    // The halo planes go straight into the neighbours' field buffers (mapped through CUDA IPC) over NVLink, followed by
-    // a 4-byte flag; no kernel takes part in the exchange, so it cannot compete with the stencil kernel for SM slots.
     // The stencil kernel's first / last march-axis chunks are scheduled last and wait in the kernel for the flag
-    // (kernel_star.cuh).  Before overwriting a neighbour's halo planes the stream waits (cuStreamWaitValue32) until that
-    // neighbour has reported the previous application finished.  Every rank takes the same decision (global extents).
+    // (kernel_star.cuh).  Every rank takes the same decision: global extents, agreed p2p state, agreed buffer mapping.
     {
         const StarLimits lim = star_limits(plan);
         const long long min_cnt = plan->dims[plan->slab_axis] / plan->nranks;
         if (ctx->p2p && plan->star && u->owned && lim.fusable && min_cnt >= lim.min_fused_planes && !getenv("DEO_DIST_NO_FUSED")) {
-            auto it = ctx->fields.find(u->ptr);
-            if (it == ctx->fields.end()) {                       // first use of this field buffer: collective registration
-                DEO_CUDA(cudaStreamSynchronize(R.stream));
-                PeerField pf;
-                int32_t rc = map_neighbours(ctx, u->ptr, &pf.lo, &pf.hi);
-                if (rc) return rc;
-                it = ctx->fields.emplace(u->ptr, pf).first;
-            }
-            const PeerField& pf = it->second;
-            const int step = ++ctx->step;
-            const size_t plane_b = plane * es;
-            CUstream cs = (CUstream)R.comm_stream;
-            DEO_CUDA(cudaEventRecord(ctx->ev_ready, R.stream));
-            DEO_CUDA(cudaStreamWaitEvent(R.comm_stream, ctx->ev_ready, 0));
-            if (has_lo) {
-                int64_t s_lo = 0, c_lo = 0;
-                deo_dist_slab(plan->dims[plan->slab_axis], plan->nranks, lo, &s_lo, &c_lo);
-                if (wait_value32()(cs, (CUdeviceptr)(ctx->flags + F_LOW_DONE), (cuuint32_t)(step - 1), CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) { set_error("cuStreamWaitValue32 failed"); return DEO_ERR_CUDA; }
-                DEO_CUDA(cudaMemcpyAsync((char*)pf.lo + (size_t)(H + c_lo) * plane_b, base + (size_t)H * plane_b, (size_t)H * plane_b, cudaMemcpyDefault, R.comm_stream));
-            }
-            if (has_hi) {
-                if (wait_value32()(cs, (CUdeviceptr)(ctx->flags + F_HIGH_DONE), (cuuint32_t)(step - 1), CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) { set_error("cuStreamWaitValue32 failed"); return DEO_ERR_CUDA; }
-                DEO_CUDA(cudaMemcpyAsync((char*)pf.hi, base + (size_t)cnt * plane_b, (size_t)H * plane_b, cudaMemcpyDefault, R.comm_stream));
-            }
-            if (write_value32()(cs, (CUdeviceptr)(ctx->flags + F_STEPWORD), (cuuint32_t)step, CU_STREAM_WRITE_VALUE_DEFAULT) != CUDA_SUCCESS) { set_error("cuStreamWriteValue32 failed"); return DEO_ERR_CUDA; }
-            if (has_lo) DEO_CUDA(cudaMemcpyAsync(ctx->lo_flags + F_HALO_FROM_HIGH, ctx->flags + F_STEPWORD, sizeof(int), cudaMemcpyDefault, R.comm_stream));
-            if (has_hi) DEO_CUDA(cudaMemcpyAsync(ctx->hi_flags + F_HALO_FROM_LOW, ctx->flags + F_STEPWORD, sizeof(int), cudaMemcpyDefault, R.comm_stream));
-            int32_t rc = launch_star_fused(plan, du->ptr, u->ptr, cnt, R.stream, ctx->flags, step, (has_lo ? 1 : 0) | (has_hi ? 2 : 0));
+            const PeerField* pf = nullptr;
+            rc = peer_field(ctx, u->ptr, &pf);
             if (rc) return rc;
-            g_launches += 1;
-            // tell the neighbours this application is finished here (they may overwrite my halo planes)
-            CUstream ks = (CUstream)R.stream;
-            if (write_value32()(ks, (CUdeviceptr)(ctx->flags + F_ACKWORD), (cuuint32_t)step, CU_STREAM_WRITE_VALUE_DEFAULT) != CUDA_SUCCESS) { set_error("cuStreamWriteValue32 failed"); return DEO_ERR_CUDA; }
-            if (has_lo) DEO_CUDA(cudaMemcpyAsync(ctx->lo_flags + F_HIGH_DONE, ctx->flags + F_ACKWORD, sizeof(int), cudaMemcpyDefault, R.stream));
-            if (has_hi) DEO_CUDA(cudaMemcpyAsync(ctx->hi_flags + F_LOW_DONE, ctx->flags + F_ACKWORD, sizeof(int), cudaMemcpyDefault, R.stream));
-            return DEO_OK;
+            if (pf->ok) {
+                const int step = ++ctx->step;
+                DEO_CUDA(cudaEventRecord(ctx->ev_ready, R.stream));
+                rc = push_halos(ctx, plan, *pf, base, step, ctx->ev_ready, ctx->ev_ready);
+                if (rc) return rc;
+                rc = launch_star_fused(plan, du->ptr, u->ptr, cnt, R.stream, ctx->flags, step, (has_lo ? 1 : 0) | (has_hi ? 2 : 0));
+                if (rc) return rc;
+                g_launches += 1;
+                return ack_done(ctx, plan, step, R.stream);
+            }
         }
     }
     // exchange on the communication stream, after everything already queued on the compute stream (u may be its output)
@@ -322,7 +394,7 @@ int32_t dist_apply(deo_plan* plan, deo_buffer* du, deo_buffer* u) {
     // planes that read no halo run concurrently with the exchange
     const long long z_lo = has_lo ? (H < cnt ? H : cnt) : 0;
     const long long z_hi = has_hi ? (cnt - H > z_lo ? cnt - H : z_lo) : cnt;
-    int32_t rc = launch_plan(plan, du->ptr, u->ptr, z_lo, z_hi, R.stream);
+    rc = launch_plan(plan, du->ptr, u->ptr, z_lo, z_hi, R.stream);
     if (rc) return rc;
     DEO_CUDA(cudaStreamWaitEvent(R.stream, ctx->ev_halo, 0));
     rc = launch_plan(plan, du->ptr, u->ptr, 0, z_lo, R.stream);
@@ -330,6 +402,112 @@ int32_t dist_apply(deo_plan* plan, deo_buffer* du, deo_buffer* u) {
     rc = launch_plan(plan, du->ptr, u->ptr, z_hi, cnt, R.stream);
     g_launches += (z_hi > z_lo) + (z_lo > 0) + (cnt > z_hi);
     return rc;
+}
+
+// Host-buffer form of mul! on a slab: u_own / du_host hold this rank's `count` planes.  Chunks of planes go through
+// upload | kernel | download on three streams like deo_plan_apply_host; the two edge chunks are uploaded first so that
+// the halo pushes to the neighbours start at once, and computed last, behind a stream wait on the neighbours' flags.
+int32_t dist_apply_host(deo_plan* plan, void* du_host, const void* u_own) {
+    DEO_REQUIRE(plan && du_host && u_own, "deo_dist_plan_apply_host: null argument");
+    DEO_REQUIRE(plan->slab_axis >= 0, "deo_dist_plan_apply_host: not a slab plan");
+    DEO_REQUIRE(plan->dist != nullptr || plan->nranks == 1, "deo_dist_plan_apply_host: the plan has no communicator (deo_dist_plan_create_local plans take device buffers)");
+    Runtime& R = rt();
+    deo_dist* ctx = plan->dist;
+    const size_t in_b = plan->in_elems() * plan->elem(), out_b = plan->out_elems() * plan->elem();
+    int32_t rc = DEO_OK;
+    if (!plan->host_u) { rc = deo_buffer_create(in_b, &plan->host_u); if (rc) return rc; }
+    if (!plan->host_du) { rc = deo_buffer_create(out_b, &plan->host_du); if (rc) return rc; }
+    deo_buffer *u = plan->host_u, *du = plan->host_du;
+    const int H = plan->halo;
+    const long long cnt = plan->slab_count;
+    const size_t plane_b = (size_t)plan->in_dim(0) * (size_t)plan->in_dim(1) * plan->elem();   // in and out planes are equal (no x/y padding)
+    char* ub = (char*)u->ptr + (size_t)H * plane_b;                                           // own planes start here
+    const bool has_lo = plan->rank > 0, has_hi = plan->rank + 1 < plan->nranks;
+    // chunking (same rule on every rank would not be needed: the exchange only involves the edge planes)
+    int reach = 0;
+    for (const HostOp& h : plan->ops)
+        if (h.d.axis == plan->slab_axis) reach = reach > h.d.boundary_stencil_length ? reach : h.d.boundary_stencil_length;
+    const size_t chunk_bytes = getenv("DEO_HOST_CHUNK_BYTES") ? (size_t)atoll(getenv("DEO_HOST_CHUNK_BYTES")) : ((size_t)96 << 20);
+    long long chunk = (long long)(chunk_bytes / (plane_b ? plane_b : 1));
+    if (chunk < 2 * reach + 8) chunk = 2 * reach + 8;
+    if (chunk < 2 * H) chunk = 2 * H;
+    std::vector<long long> zb;
+    for (long long z = 0; z < cnt; z += chunk) zb.push_back(z);
+    if (zb.size() > 1 && cnt - zb.back() < 2 * reach + 2) zb.pop_back();
+    zb.push_back(cnt);
+    const long long nchunks = (long long)zb.size() - 1;
+    const PeerField* pf = nullptr;
+    bool p2p = ctx && plan->nranks > 1 && H > 0 && ctx->p2p;
+    if (p2p) {
+        rc = peer_field(ctx, u->ptr, &pf);
+        if (rc) return rc;
+        p2p = pf->ok;
+    }
+    const bool single = !ctx || plan->nranks == 1 || H == 0;
+    if (nchunks < 3 || !(p2p || single)) {
+        // serial: upload, the device-resident application (whatever exchange schedule it picks), download
+        DEO_CUDA(cudaMemcpyAsync(ub, u_own, out_b, cudaMemcpyHostToDevice, R.stream));
+        rc = dist_apply(plan, du, u);
+        if (rc) return rc;
+        DEO_CUDA(cudaMemcpyAsync(du_host, du->ptr, out_b, cudaMemcpyDeviceToHost, R.stream));
+        DEO_CUDA(cudaStreamSynchronize(R.stream));
+        DEO_CUDA(cudaStreamSynchronize(R.comm_stream));
+        return DEO_OK;
+    }
+    while ((long long)plan->host_ev.size() < 2 * nchunks) {
+        cudaEvent_t e;
+        DEO_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        plan->host_ev.push_back(e);
+    }
+    DEO_CUDA(cudaStreamSynchronize(R.stream));
+    rc = clear_outer_halos(plan, u->ptr, R.h2d_stream);
+    if (rc) return rc;
+    // upload order: first chunk, last chunk, then the middle ones
+    std::vector<long long> order;
+    order.push_back(0);
+    order.push_back(nchunks - 1);
+    for (long long k = 1; k + 1 < nchunks; ++k) order.push_back(k);
+    for (long long k : order) {
+        const long long z0 = zb[(size_t)k], z1 = zb[(size_t)k + 1];
+        DEO_CUDA(cudaMemcpyAsync(ub + (size_t)z0 * plane_b, (const char*)u_own + (size_t)z0 * plane_b, (size_t)(z1 - z0) * plane_b, cudaMemcpyHostToDevice, R.h2d_stream));
+        DEO_CUDA(cudaEventRecord(plan->host_ev[(size_t)k], R.h2d_stream));
+    }
+    int step = 0;
+    if (!single) {
+        step = ++ctx->step;
+        rc = push_halos(ctx, plan, *pf, (char*)u->ptr, step, plan->host_ev[0], plan->host_ev[(size_t)nchunks - 1]);
+        if (rc) return rc;
+    }
+    // kernels: middle chunks in order (chunk k reads into chunks k-1 and k+1), then the two edge chunks
+    std::vector<long long> korder;
+    for (long long k = 1; k + 1 < nchunks; ++k) korder.push_back(k);
+    korder.push_back(0);
+    korder.push_back(nchunks - 1);
+    for (long long k : korder) {
+        const long long z0 = zb[(size_t)k], z1 = zb[(size_t)k + 1];
+        const long long dep = k + 1 < nchunks - 1 ? k + 1 : k;               // uploads are in order: the latest middle chunk read covers the earlier ones
+        DEO_CUDA(cudaStreamWaitEvent(R.stream, plan->host_ev[(size_t)(k == 0 ? (nchunks > 2 ? 1 : 0) : (k == nchunks - 1 ? nchunks - 2 : dep))], 0));
+        if (k == nchunks - 1) DEO_CUDA(cudaStreamWaitEvent(R.stream, plan->host_ev[(size_t)k], 0));
+        if (!single && k == 0 && has_lo)
+            DEO_DRV(wait_value32()((CUstream)R.stream, (CUdeviceptr)(ctx->flags + F_HALO_FROM_LOW), (cuuint32_t)step, CU_STREAM_WAIT_VALUE_GEQ), "cuStreamWaitValue32");
+        if (!single && k == nchunks - 1 && has_hi)
+            DEO_DRV(wait_value32()((CUstream)R.stream, (CUdeviceptr)(ctx->flags + F_HALO_FROM_HIGH), (cuuint32_t)step, CU_STREAM_WAIT_VALUE_GEQ), "cuStreamWaitValue32");
+        rc = launch_plan(plan, du->ptr, u->ptr, z0, z1, R.stream);
+        if (rc) return rc;
+        g_launches += 1;
+        DEO_CUDA(cudaEventRecord(plan->host_ev[(size_t)(nchunks + k)], R.stream));
+        DEO_CUDA(cudaStreamWaitEvent(R.d2h_stream, plan->host_ev[(size_t)(nchunks + k)], 0));
+        DEO_CUDA(cudaMemcpyAsync((char*)du_host + (size_t)z0 * plane_b, (const char*)du->ptr + (size_t)z0 * plane_b, (size_t)(z1 - z0) * plane_b,
+                                 cudaMemcpyDeviceToHost, R.d2h_stream));
+    }
+    if (!single) {
+        rc = ack_done(ctx, plan, step, R.stream);
+        if (rc) return rc;
+    }
+    DEO_CUDA(cudaStreamSynchronize(R.d2h_stream));
+    DEO_CUDA(cudaStreamSynchronize(R.stream));
+    DEO_CUDA(cudaStreamSynchronize(R.comm_stream));
+    return DEO_OK;
 }
 
 }  // namespace
@@ -370,17 +548,27 @@ int32_t deo_dist_init(const void* id_bytes, int32_t rank, int32_t nranks, deo_di
     ctx->nranks = nranks;
     DEO_CUDA(cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming));
     DEO_CUDA(cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming));
-    // peer-to-peer exchange state; any failure here (IPC not permitted, stream memory operations missing) leaves the
-    // NCCL send/recv schedule in charge
-    if (!getenv("DEO_DIST_NO_P2P") && wait_value32() && write_value32() && nranks > 1) {
-        bool ok = cudaMalloc(&ctx->flags, F_COUNT * sizeof(int)) == cudaSuccess && cudaMemset(ctx->flags, 0, F_COUNT * sizeof(int)) == cudaSuccess &&
-                  cudaMalloc(&ctx->xbuf, 192) == cudaSuccess;
-        void *lf = nullptr, *hf = nullptr;
-        ok = ok && cudaDeviceSynchronize() == cudaSuccess && map_neighbours(ctx.get(), ctx->flags, &lf, &hf) == DEO_OK;
-        ctx->lo_flags = (int*)lf;
-        ctx->hi_flags = (int*)hf;
-        ctx->p2p = ok;
+    DEO_CUDA(cudaMalloc(&ctx->abuf, 2 * sizeof(int)));
+    // peer-to-peer exchange state.  Every step that can fail on one rank only (allocation, IPC export / import, missing
+    // stream memory operations) is followed by an agreement over all ranks, so either every rank ends with p2p == true
+    // or every rank leaves the NCCL send/recv schedule in charge.
+    if (nranks > 1) {
+        bool ok = !getenv("DEO_DIST_NO_P2P") && wait_value32() && write_value32();
+        ok = ok && cudaMalloc(&ctx->flags, F_COUNT * sizeof(int)) == cudaSuccess && cudaMemset(ctx->flags, 0, F_COUNT * sizeof(int)) == cudaSuccess &&
+             cudaMalloc(&ctx->xbuf, 192) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess;
         if (!ok) cudaGetLastError();
+        bool all = false;
+        rc = agree(ctx.get(), ok, &all);
+        if (rc) return rc;
+        if (all) {
+            void *lf = nullptr, *hf = nullptr;
+            bool mapped = false;
+            rc = map_neighbours(ctx.get(), ctx->flags, &lf, &hf, &mapped);
+            if (rc) return rc;
+            ctx->lo_flags = (int*)lf;
+            ctx->hi_flags = (int*)hf;
+            ctx->p2p = mapped;
+        }
     }
     *out = ctx.release();
     g_contexts.push_back(*out);
@@ -399,6 +587,7 @@ int32_t deo_dist_destroy(deo_dist* ctx) {
     if (ctx->hi_flags) cudaIpcCloseMemHandle(ctx->hi_flags);
     if (ctx->flags) cudaFree(ctx->flags);
     if (ctx->xbuf) cudaFree(ctx->xbuf);
+    if (ctx->abuf) cudaFree(ctx->abuf);
     delete ctx;
     return DEO_OK;
 }
@@ -419,6 +608,8 @@ int32_t deo_dist_plan_halo(const deo_plan* plan, int32_t* halo) {
 }
 
 int32_t deo_dist_plan_apply(deo_plan* plan, deo_buffer* du, deo_buffer* u) { return dist_apply(plan, du, u); }
+
+int32_t deo_dist_plan_apply_host(deo_plan* plan, void* du_host, const void* u_own_host) { return dist_apply_host(plan, du_host, u_own_host); }
 
 int32_t deo_dist_plan_time(deo_plan* plan, deo_buffer* du, deo_buffer* u, int32_t reps, float* ms_per_apply) {
     DEO_REQUIRE(reps >= 1 && ms_per_apply, "deo_dist_plan_time: bad arguments");

@@ -139,7 +139,14 @@ int32_t deo_buffer_wrap(void* devptr, size_t bytes, deo_buffer** out) {
 int32_t deo_buffer_free(deo_buffer* buf) {
     if (!buf) return DEO_OK;
     if (buf->owned && buf->ptr) {
-        cudaStreamSynchronize(rt().stream);
+        // nothing of ours may still be reading or writing the allocation: the compute stream, the halo pushes / NCCL
+        // transfers of the communication stream and the chunk pipeline's copy streams
+        if (rt().ready) {
+            cudaStreamSynchronize(rt().stream);
+            cudaStreamSynchronize(rt().comm_stream);
+            cudaStreamSynchronize(rt().h2d_stream);
+            cudaStreamSynchronize(rt().d2h_stream);
+        }
         deo::dist_forget_buffer(buf->ptr);
         cudaFree(buf->ptr);
     }

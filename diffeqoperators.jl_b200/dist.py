@@ -103,6 +103,13 @@ class SlabPlan(Plan):
     def apply(self, du: DeviceArray, u_ext: DeviceArray):
         _lib.check(_lib.load().deo_dist_plan_apply(self._h, du._h, u_ext._h))
 
+    def apply_host(self, du_host: np.ndarray, u_ext_host: np.ndarray):
+        """Host-buffer form on a slab: `u_ext_host` is this rank's [halo | own planes | halo] block (only the own planes
+        are read), `du_host` its `count` output planes."""
+        own = u_ext_host[..., self.halo:self.halo + self.count] if self.halo else u_ext_host
+        assert own.flags.f_contiguous and du_host.flags.f_contiguous
+        _lib.check(_lib.load().deo_dist_plan_apply_host(self._h, du_host.ctypes.data_as(C.c_void_p), own.ctypes.data_as(C.c_void_p)))
+
     def time(self, du: DeviceArray, u_ext: DeviceArray, reps: int) -> float:
         ms = C.c_float(0)
         _lib.check(_lib.load().deo_dist_plan_time(self._h, du._h, u_ext._h, reps, C.byref(ms)))

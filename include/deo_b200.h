@@ -160,6 +160,10 @@ int32_t deo_dist_plan_halo(const deo_plan *plan, int32_t *halo);
 /* Halo exchange (ncclSend/ncclRecv to both slab neighbours on a communication stream) overlapped
  * with the interior planes; boundary planes follow.  u: extended local buffer, du: count planes. */
 int32_t deo_dist_plan_apply(deo_plan *plan, deo_buffer *du, deo_buffer *u);
+/* Host-buffer form of mul! on a slab (the multi-GPU counterpart of deo_plan_apply_host): u_own_host and du_host
+ * hold this rank's `count` planes (no halo).  Chunks of planes are uploaded, computed and downloaded on three
+ * streams; the edge chunks go up first so that the halo pushes to the neighbours overlap the rest.  Synchronous. */
+int32_t deo_dist_plan_apply_host(deo_plan *plan, void *du_host, const void *u_own_host);
 int32_t deo_dist_plan_time(deo_plan *plan, deo_buffer *du, deo_buffer *u, int32_t reps, float *ms_per_apply);
 /* Single-process emulation used by the tests: build rank `rank` of `nranks`' local plan without NCCL;
  * the caller fills the halo planes itself. */

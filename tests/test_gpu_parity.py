@@ -518,56 +518,3 @@ def test_slab_plans_reassemble_the_global_result(D, O, nranks):
             D._lib.check(D._lib.load().deo_dist_plan_apply(plan._h, dud._h, ud._h))
             out[:, :, s:s + c] = dud.to_host()
         assert_close(out, want, np.float64, f"slabs P={nranks} a={a}")
-
-
-# ------------------------------------------------------------------------------------------------------
-# size-independent properties at BASELINE's full sizes (the oracle is too slow there)
-# ------------------------------------------------------------------------------------------------------
-def _full_size_properties(D, A, Q, shape, dtype, tol):
-    rng = np.random.default_rng(7)
-    G = A * Q
-    u = D.DeviceArray.from_host(np.asfortranarray(rng.uniform(-1, 1, shape).astype(dtype)))
-    v = D.DeviceArray.from_host(np.asfortranarray(rng.uniform(-1, 1, shape).astype(dtype)))
-    z = D.DeviceArray.from_host(np.zeros(shape, dtype=dtype, order="F"))
-    Gu, Gv, G0 = (G * u).to_host(), (G * v).to_host(), (G * z).to_host()
-    # affine-linearity: G(u + v) - G(0) == (G(u) - G(0)) + (G(v) - G(0)) up to rounding
-    w = D.DeviceArray.from_host(np.asfortranarray(u.to_host() + v.to_host()))
-    Gw = (G * w).to_host()
-    scale = max(np.abs(Gu).max(), np.abs(Gv).max())
-    assert np.abs((Gw - G0) - ((Gu - G0) + (Gv - G0))).max() <= tol * scale
-    # idempotence of the call (same input -> bit-identical output) and the generic kernel as cross-check
-    assert np.array_equal((G * u).to_host(), Gu)
-    gen = D.mul_alloc(G, u, flags=D._lib.DEO_FLAG_FORCE_GENERIC).to_host()
-    assert np.abs(gen - Gu).max() <= tol * scale
-    return Gu
-
-
-def test_full_size_config2_properties(D):
-    shape = (8192, 8192)
-    h = (1.0 / 8193, 1.0 / 8193)
-    A, _ = _laplacian_pair(shape, 4, h, np.float64)
-    Q = D.compose(*D.RobinBC((1.0, 0.5, 0.25), (1.0, -0.5, 0.75), h, 1, shape))
-    _full_size_properties(D, A, Q, shape, np.float64, 1e-13)
-
-
-@pytest.mark.parametrize("dtype", DTYPES)
-def test_full_size_config3_properties(D, O, dtype):
-    shape = (512, 512, 512)
-    h = (1.0 / 513,) * 3
-    A, Bs = _laplacian_pair(shape, 6, h, dtype)
-    Q = D.compose(*D.Neumann0BC(dtype, h, 1, shape))
-    Gu = _full_size_properties(D, A, Q, shape, dtype, TOL[np.dtype(dtype)])
-    # and a thin oracle check: the first and last 6 planes against the oracle on a z-truncated problem is not
-    # equivalent (BC at the cut), so instead compare one x-y sub-block pencil-wise along x on a slice
-    rng = np.random.default_rng(7)
-    u = np.asfortranarray(rng.uniform(-1, 1, shape).astype(dtype))
-    sub = (slice(0, 512), slice(100, 101), slice(200, 201))
-    # x-op + y-op + z-op at the points of one x-pencil, from the oracle's 1-D pieces
-    bc = O.Neumann0BC(h[0], 1, dtype)
-    L1 = O.CenteredDifference(2, 6, h[0], 512, dtype=dtype)
-    px = O.apply_axis(L1, u[:, 100, 200].copy(), bc)
-    py = np.array([O.apply_axis(L1, u[i, :, 200].copy(), bc)[100] for i in range(0, 512, 37)])
-    pz = np.array([O.apply_axis(L1, u[i, 100, :].copy(), bc)[200] for i in range(0, 512, 37)])
-    want = (px[::37] + py) + pz
-    got = Gu[sub].reshape(-1)[::37]
-    assert rel_err(got, want) <= TOL[np.dtype(dtype)] * 10
