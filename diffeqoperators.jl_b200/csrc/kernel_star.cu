@@ -1,7 +1,7 @@
 // Host side of the tiled streaming kernel (kernel_star.cuh): eligibility, parameter packing, tensor map, dispatch.
 #include <cstdlib>
 
-#include "kernel_star.cuh"
+#include "kernel_star2.cuh"
 
 namespace deo {
 
@@ -25,7 +25,20 @@ PFN_encodeTiled get_encode() {
 
 
 template <typename T>
+int32_t dispatch2_T(const StarConfig& C, const void* u, void* du, long long z0, long long z1, cudaStream_t s) {
+    switch (C.R) {
+        case 1: return star2_launch_R<T, 1>(C, u, du, z0, z1, s);
+        case 2: return star2_launch_R<T, 2>(C, u, du, z0, z1, s);
+        case 3: return star2_launch_R<T, 3>(C, u, du, z0, z1, s);
+        case 4: return star2_launch_R<T, 4>(C, u, du, z0, z1, s);
+    }
+    set_error("star kernel: unsupported radius %d", C.R);
+    return DEO_ERR_UNSUPPORTED;
+}
+
+template <typename T>
 int32_t dispatch_T(const StarConfig& C, const void* u, void* du, long long z0, long long z1, cudaStream_t s) {
+    if (C.v2) return dispatch2_T<T>(C, u, du, z0, z1, s);
     switch (C.R) {
         case 1: return star_launch_R<T, 1>(C, u, du, z0, z1, s);
         case 2: return star_launch_R<T, 2>(C, u, du, z0, z1, s);
@@ -246,12 +259,38 @@ bool fill_params_R(const deo_plan* plan, const int kaxis[3], bool mid, StarConfi
 
 }  // namespace
 
+Star2Runtime& star2_rt() {
+    static Star2Runtime r;
+    if (!r.err_host) {
+        if (cudaHostAlloc((void**)&r.err_host, sizeof(int), cudaHostAllocMapped) == cudaSuccess &&
+            cudaHostGetDevicePointer((void**)&r.err_dev, r.err_host, 0) == cudaSuccess) {
+            *r.err_host = 0;
+            if (cudaMalloc((void**)&r.sched, 2 * sizeof(unsigned int)) != cudaSuccess || cudaMemset(r.sched, 0, 2 * sizeof(unsigned int)) != cudaSuccess) {
+                cudaGetLastError();
+                r.sched = nullptr;
+            }
+        } else {
+            cudaGetLastError();
+            r.err_host = nullptr; r.err_dev = nullptr;
+        }
+    }
+    return r;
+}
+
+// Set (and cleared here) when a slab launch gave up waiting for its neighbours' halo planes.
+bool star_take_halo_timeout() {
+    Star2Runtime& r = star2_rt();
+    if (r.err_host && *(volatile int*)r.err_host) { *(volatile int*)r.err_host = 0; return true; }
+    return false;
+}
+
 // The tile geometry must contain everything the x / y edge paths read (boundary stencils and BC stencils).
 static bool tile_fits(const deo_plan* plan, const StarConfig& cfg, bool mid) {
     const size_t es = plan->elem();
     const int R = cfg.R;
     const int VEC = (int)(16 / es), HXh = ((R + VEC - 1) / VEC) * VEC, TB = 2 * R + 2;
-    const int TX = mid ? 32 * VEC : 32 * VEC * cfg.nwy * cfg.py, TY = cfg.nwy * cfg.py;
+    const int nwy = cfg.v2 ? 16 : cfg.nwy, py = cfg.v2 ? 2 : cfg.py;
+    const int TX = mid ? 32 * VEC : 32 * VEC * nwy * py, TY = nwy * py;
     const long long nx = plan->dims[0], ny = mid ? plan->dims[1] : 1;
     const int wlast = (int)((nx - 1) % TX) + 1, hlast = (int)((ny - 1) % TY) + 1;
     const int Kx = plan->bc[0].d.K_r, Ky = mid ? plan->bc[1].d.K_r : 0;
@@ -287,6 +326,9 @@ int32_t star_configure(deo_plan* plan) {
     cfg->zchunk_max = getenv("DEO_STAR_ZCHUNK") ? atoi(getenv("DEO_STAR_ZCHUNK")) : 32;
     cfg->l2promo = getenv("DEO_TMA_L2PROMO") ? atoi(getenv("DEO_TMA_L2PROMO")) : 3;
     cfg->group = getenv("DEO_STAR_GROUP") ? atoi(getenv("DEO_STAR_GROUP")) : -1;   // measured: the plain order is fastest
+    cfg->v2 = !(getenv("DEO_STAR_V") && atoi(getenv("DEO_STAR_V")) == 1);            // A/B: DEO_STAR_V=1 selects the first-generation kernel
+    if (getenv("DEO_HALO_TIMEOUT_S") && atof(getenv("DEO_HALO_TIMEOUT_S")) > 0)
+        cfg->halo_timeout_ns = (unsigned long long)(atof(getenv("DEO_HALO_TIMEOUT_S")) * 1e9);
 
     // ---- CONST eligibility ----
     bool const_ok = plan->ops.size() <= 3 && !getenv("DEO_STAR_FORCE_TABLE");
@@ -368,7 +410,8 @@ int32_t launch_star(const deo_plan* plan, void* du, const void* u, long long z0,
     const int VEC = (int)(16 / es);
     const int HX = ((C.R + VEC - 1) / VEC) * VEC;
     cuuint32_t box[3];
-    if (mid) { box[0] = (cuuint32_t)(32 * VEC + 2 * HX); box[1] = (cuuint32_t)(C.nwy * C.py + 2 * C.R); box[2] = 1; }
+    const int tile_rows = C.v2 ? 32 : C.nwy * C.py;
+    if (mid) { box[0] = (cuuint32_t)(32 * VEC + 2 * HX); box[1] = (cuuint32_t)(tile_rows + 2 * C.R); box[2] = 1; }
     else { box[0] = 256; box[1] = 1; box[2] = 1; }
     const int promo_env = C.l2promo;
     const CUtensorMapL2promotion promo = promo_env == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo_env == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B

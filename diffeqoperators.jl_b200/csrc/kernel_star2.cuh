@@ -1,0 +1,756 @@
+// Persistent, warp-specialised tiled streaming kernel (second generation of kernel_star.cuh; same operand structures,
+// same arithmetic, same results bit for bit).
+//
+//   * ONE CTA per SM, persistent: 16 compute warps + 1 helper warp; the CTA walks a list of work items
+//     (x-y tile, march-axis chunk) and the helper keeps the TMA ring full ACROSS item boundaries, so there is no
+//     per-chunk pipeline fill / drain bubble and no co-resident CTA is needed to hide one.
+//   * compute warps run ONE code path for every tile: the 2.5-D register queue always rotates by renaming (the loop
+//     is unrolled 2R+1 times), there is no face code in it.  Rows whose stencil touches an x / y ghost (one-sided
+//     boundary rows, convolutions.jl:76-118, and the interior rows next to them) are evaluated by the HELPER warp
+//     straight from the shared-memory plane as soon as it has landed -- the affine ghost b + a.u[edge]
+//     (bc_operators.jl:188-191) included -- and parked in the plane's own halo cells (which hold nothing but the
+//     TMA's out-of-bounds zeros on a face tile); the owning compute lane picks the value up with one predicated
+//     load.  A `fixed` mbarrier per ring slot orders the two.
+//   * tile = 32*VEC x 32 points (Float64 64 x 32, Float32 128 x 32): 34 % halo instead of the 55 % of 64 x 16 tiles.
+//   * the march-axis faces stay with the compute warps (the register queue holds exactly the planes those rows
+//     need); only the few steps next to a march-axis face run the shifted-queue edge step.
+//
+// Arithmetic: acc = fma(w[t], q[t], acc) over the taps in the reference's order (idx = 1..sl), operators summed in
+// A.ops order, w = (c*w) pre-multiplied as the reference forms it (convolutions.jl:47).
+#pragma once
+#include "kernel_star.cuh"
+
+namespace deo {
+
+struct Star2Launch {
+    int z_begin, z_end, zchunk, nchunks;
+    int tiles_x, tiles_xy, n_items, fused;
+    const int* halo_flag;            // slab plans: [0] low side, [1] high side, written over NVLink after the halo planes
+    int halo_expect, halo_sides;
+    int* err_word;                   // mapped host word: set when the halo wait expires (the host turns it into DEO_ERR_CUDA)
+    unsigned long long timeout_ns;
+    unsigned int* sched;             // [0] next work item (dynamic scheduling), [1] CTAs finished; both return to 0 at the end of a launch
+    int accumulate, axpy;            // du += result (overwrite = false);  du = u + dt * result
+    double dt;
+};
+
+template <typename T, int R, bool MID>
+struct Star2Geom {
+    static constexpr int VEC = Vec<T>::N;
+    static constexpr int NW = 16, PY = 2;
+    static constexpr int HX = ((R + VEC - 1) / VEC) * VEC;        // x halo rounded up: every window load is one 16 B vector
+    static constexpr int TX = MID ? 32 * VEC : 32 * VEC * NW * PY;
+    static constexpr int TY = MID ? NW * PY : 1;
+    static constexpr int PITCH = TX + 2 * HX;
+    static constexpr int ROWS = MID ? TY + 2 * R : 1;
+    static constexpr int BOXW = 256;                              // TMA box limit per dimension (elements)
+    static constexpr int NBOX = MID ? 1 : (PITCH + BOXW - 1) / BOXW;
+    static constexpr int PLANE = MID ? PITCH * ROWS : NBOX * BOXW;   // elements written per plane
+    static constexpr int PLANE_BYTES = ((PLANE * (int)sizeof(T) + 127) / 128) * 128;
+    static constexpr int NS_FIT = (216 * 1024) / PLANE_BYTES;
+    static constexpr int NS_CAP = R + 12;
+    static constexpr int NS = NS_FIT < NS_CAP ? NS_FIT : NS_CAP;
+    static constexpr int NQ = 2 * R + 1;
+    static constexpr int THREADS = (NW + 4) * 32;                 // 4 compute warpgroups + 1 helper warpgroup (producer + 3 evaluators)
+    // Register split (setmaxnreg).  The launch allocates 640 * 96 registers to the CTA; setmaxnreg.inc can only draw on
+    // what setmaxnreg.dec returned to that per-CTA pool: the helper warpgroup gives back 128 * (96 - 32) = 8192, the four
+    // compute warpgroups take 512 * (112 - 96) = 8192.
+    static constexpr int REGS_COMPUTE = 112, REGS_HELPER = 32;
+    static_assert(512 * (REGS_COMPUTE - 96) <= 128 * (96 - REGS_HELPER), "setmaxnreg: the per-CTA register pool would run dry (deadlock)");
+    static constexpr int NIQ = 8;                                 // item queue entries (the producer is never more than 3 items ahead)
+    static constexpr size_t SMEM = (size_t)NS * PLANE_BYTES + (3 * NS + NIQ) * sizeof(uint64_t) + NIQ * sizeof(int) + 64;
+    static_assert(NS >= R + 4, "ring too small");
+};
+
+__device__ __forceinline__ bool mbar_test_u32(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// f(false_type, integral_constant<int, U>) for U = 0 .. N-1, leaving early (returns true) as soon as stop() holds
+template <int N, int U = 0, class F, class Stop>
+__device__ __forceinline__ bool rot_steps(F& f, Stop& stop) {
+    f(std::false_type{}, std::integral_constant<int, U>{});
+    if (stop()) return true;
+    if constexpr (U + 1 < N) return rot_steps<N, U + 1>(f, stop);
+    else return false;
+}
+
+// One work item: tile origin and march-axis range.  Items are ordered chunk-major (every tile of chunk 0, then chunk
+// 1, ...): the CTAs of the grid work on neighbouring tiles of the same chunk at the same time, so the halo
+// rows / columns two tiles share are still in L2 when the second one asks.  Slab launches that wait for their halo
+// planes in the kernel schedule the first and the last chunk last.
+struct Star2Item { int tx0, ty0, zc0, zc1; };
+template <int TX, int TY, bool MID>
+__device__ __forceinline__ Star2Item star2_item(const Star2Launch& L, int it) {
+    int chunk = it / L.tiles_xy;
+    const int tile = it - chunk * L.tiles_xy;
+    if (L.fused) chunk = chunk < L.nchunks - 2 ? chunk + 1 : (chunk == L.nchunks - 2 ? 0 : L.nchunks - 1);
+    Star2Item I;
+    I.tx0 = (tile % L.tiles_x) * TX;
+    I.ty0 = MID ? (tile / L.tiles_x) * TY : 0;
+    I.zc0 = L.z_begin + chunk * L.zchunk;
+    I.zc1 = min(I.zc0 + L.zchunk, L.z_end);
+    return I;
+}
+
+template <typename T, int R, bool MID, int MASK, bool TABLE>
+__global__ void __launch_bounds__(Star2Geom<T, R, MID>::THREADS, 1)
+k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarParams<T, R> S, const __grid_constant__ Star2Launch L,
+        const T* __restrict__ u, T* __restrict__ du) {
+    using G = Star2Geom<T, R, MID>;
+    constexpr int VEC = G::VEC, HX = G::HX, PITCH = G::PITCH, NS = G::NS, NQ = G::NQ, TB = 2 * R + 2, PY = G::PY, NW = G::NW;
+    constexpr int XW = VEC + 2 * R;
+    constexpr int PLANE_ELEMS = G::PLANE_BYTES / (int)sizeof(T);
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr bool has_x = (MASK & 1) != 0, has_y = MID && (MASK & 2) != 0, has_z = (MASK & 4) != 0;
+
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    T* const planes = reinterpret_cast<T*>(smem_raw);
+    uint64_t* const full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * G::PLANE_BYTES);
+    uint64_t* const empty = full + NS;
+    uint64_t* const fixedb = empty + NS;
+    uint64_t* const itemb = fixedb + NS;                       // item queue: entry q % NIQ is valid once phase q / NIQ of its barrier completes
+    volatile int* const itemq = reinterpret_cast<volatile int*>(itemb + G::NIQ);
+    const uint32_t full_u32 = smem_u32(full), empty_u32 = smem_u32(empty), fixed_u32 = smem_u32(fixedb), item_u32 = smem_u32(itemb);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NW); mbar_init(&fixedb[s], 1); }
+        for (int s = 0; s < G::NIQ; ++s) mbar_init(&itemb[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int nx = S.nx, ny = S.ny;
+    const int ex = S.nedge[0], ey = S.nedge[1], ez = S.nedge[2];
+
+    if (warp >= NW) {
+        // ============================== helper warpgroup (warps NW .. NW+3) ==============================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(G::REGS_HELPER));
+        if (warp == NW) {
+            // ---- producer: one elected lane keeps the TMA ring full, across item boundaries ----------------
+            if (lane != 0) return;
+            // Work items are handed out dynamically, in list order: whichever CTA is ready takes the next one, so the items
+            // in flight always form one contiguous window of the list -- spatial neighbours stay in step and find each
+            // other's halo rows / columns in L2 (a static assignment lets slow CTAs fall behind for good: DRAM reads x1.6).
+            // The producer publishes each item to the other warps through the item queue.
+            int g = 0, q = 0;
+            int item = blockIdx.x;
+#pragma unroll 1
+            for (;;) {
+                const bool last = item >= L.n_items;
+                itemq[q % G::NIQ] = last ? -1 : item;
+                mbar_arrive_u32(item_u32 + 8u * (q % G::NIQ));
+                ++q;
+                if (last) break;
+                const int next = (int)gridDim.x + (int)atomicAdd(L.sched, 1u);   // fetched one item ahead: its latency hides behind this item's planes
+                const Star2Item I = star2_item<G::TX, G::TY, MID>(L, item);
+                const int n = I.zc1 - I.zc0 + 2 * R;
+                if (L.halo_flag != nullptr) {
+                    // slab launch: the first / last chunk read halo planes that arrive over NVLink while the kernel runs
+                    // (these items are scheduled last).  A lost exchange raises the error word, it never hangs the GPU.
+#pragma unroll 1
+                    for (int side = 0; side < 2; ++side) {
+                        const bool need = side == 0 ? ((L.halo_sides & 1) && I.zc0 - R < L.z_begin) : ((L.halo_sides & 2) && I.zc1 + R > L.z_end);
+                        if (!need) continue;
+                        const unsigned long long t0 = global_ns();
+                        for (;;) {
+                            int seen;
+                            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(L.halo_flag + side) : "memory");
+                            if (seen - L.halo_expect >= 0) break;
+                            if (global_ns() - t0 > L.timeout_ns) {
+                                if (L.err_word) asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(L.err_word), "r"(1) : "memory");
+                                break;                 // give up waiting: this application's results are flagged invalid on the host
+                            }
+                            __nanosleep(200);
+                        }
+                    }
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                }
+#pragma unroll 1
+                for (int k = 0; k < n; ++k, ++g) {
+                    const int slot = g % NS;
+                    if (g >= NS) mbar_wait_u32(empty_u32 + 8u * slot, ((g / NS) - 1) & 1);
+                    mbar_expect_tx(&full[slot], (uint32_t)(G::PLANE * sizeof(T)));
+                    const int pz = I.zc0 - R + k + S.in_off_z;
+                    T* dst = planes + (size_t)slot * PLANE_ELEMS;
+                    if constexpr (MID) {
+                        tma_load_3d(dst, &tmap, &full[slot], I.tx0 - HX, I.ty0 - R, pz);
+                    } else {
+#pragma unroll
+                        for (int b = 0; b < G::NBOX; ++b)
+                            tma_load_3d(dst + b * G::BOXW, &tmap, &full[slot], I.tx0 - HX + b * G::BOXW, 0, pz);
+                    }
+                }
+                item = next;
+            }
+            // the last CTA to get here puts the scheduler words back to zero for the next launch (launches on a stream do
+            // not overlap, and every other CTA has made its final fetch before it counted itself as finished)
+            __threadfence();
+            if (atomicAdd(L.sched + 1, 1u) == gridDim.x - 1) { L.sched[0] = 0u; L.sched[1] = 0u; __threadfence(); }
+            return;
+        }
+        // ---- evaluators (3 warps, ring slots dealt round-robin): the x / y rows of a landed plane whose stencil touches a ghost ----
+        const int me = warp - NW - 1;
+        int g = 0;
+#pragma unroll 1
+        for (int q = 0;; ++q) {
+            mbar_wait_u32(item_u32 + 8u * (q % G::NIQ), (q / G::NIQ) & 1);
+            const int item = itemq[q % G::NIQ];
+            if (item < 0) break;
+            const Star2Item I = star2_item<G::TX, G::TY, MID>(L, item);
+            const int n = I.zc1 - I.zc0 + 2 * R;
+            const bool f_xlo = has_x && I.tx0 == 0, f_xhi = has_x && I.tx0 + G::TX >= nx;
+            const bool f_ylo = has_y && I.ty0 == 0, f_yhi = has_y && I.ty0 + G::TY >= ny;
+            const bool face = f_xlo || f_xhi || f_ylo || f_yhi;
+#pragma unroll 1
+            for (int k = 0; k < n; ++k, ++g) {
+                const int slot = g % NS;
+                // a ring slot always belongs to the same evaluator: a waiter must see EVERY phase of a barrier, in order
+                // (TMA planes can land out of order; waiting for phase m while m-1 is still open returns at once)
+                if (slot % 3 != me) continue;
+                // Chain per slot use: TMA lands (`full`) -> this warp parks the ghost-touching rows and arrives on `fixed` ->
+                // the compute warps acquire (they wait on `fixed` only) ... release (`empty`) -> the producer refills.
+                // Every use gets exactly one arrival on each barrier, so no waiter can be lapped by two phases.
+                mbar_wait_u32(full_u32 + 8u * slot, (g / NS) & 1);
+                if (face && k >= R && k < n - R) {             // only planes that become a centre plane are read by the x / y parts
+                    T* pl = planes + (size_t)slot * PLANE_ELEMS;
+                    // Register-lean on purpose (this warpgroup runs on 32 registers per thread, see REGS_HELPER): every tap is
+                    // re-read from shared memory instead of being kept in a register window.
+                    if constexpr (has_x) {
+                        // lane <-> tile row; (side, edge row i) uniform: weights come from the constant bank
+                        if (f_xlo || f_xhi) {
+#pragma unroll 1
+                            for (int rr = lane; rr < G::TY; rr += 32) {
+                                if (MID && I.ty0 + rr >= ny) continue;
+                                T* rowl = pl + (MID ? (R + rr) * PITCH : 0);      // local row
+                                const T* row = rowl + HX - I.tx0;                // row[x] = value at global x
+#pragma unroll 1
+                                for (int side = 0; side < 2; ++side) {
+                                    if (!(side ? f_xhi : f_xlo)) continue;
+                                    const int K = side ? S.K_r[0] : S.K_l[0];
+                                    const T* a = side ? S.a_r[0] : S.a_l[0];
+                                    const T* arow = row + (side ? nx - K : 0);
+                                    T gh = T(0);
+#pragma unroll 1
+                                    for (int kk = 0; kk < K; ++kk) gh = fma_t(a[kk], arow[kk], gh);
+                                    gh += side ? S.b_r[0] : S.b_l[0];
+                                    const T* qrow = side ? row + (nx + 1 - TB) : row - 1;   // qrow[k] = q[k] (low) / q[n+2-TB+k] (high)
+                                    const int kg = side ? TB - 1 : 0;                       // the tap that is the ghost
+#pragma unroll 1
+                                    for (int i = 0; i < ex; ++i) {
+                                        const T* w = S.bw[0][side][i];
+                                        T res = T(0);
+#pragma unroll 1
+                                        for (int kk = 0; kk < TB; ++kk) res = fma_t(w[kk], kk == kg ? gh : qrow[kk], res);
+                                        // low: the value of x = i is parked HX columns to the left of its owner (local column i);
+                                        // high: the value of x = nx-ex+i HX columns to the right of its owner
+                                        if (!side) rowl[i] = res;
+                                        else rowl[(nx - ex + i) - I.tx0 + 2 * HX] = res;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    if constexpr (has_y) {
+                        // lane <-> one 16-byte vector of columns: conflict-free vector loads
+                        if (f_ylo || f_yhi) {
+                            T* colbase = pl + (R - I.ty0) * PITCH + HX + lane * VEC;      // colbase[y*PITCH + v] = value at global row y
+#pragma unroll 1
+                            for (int side = 0; side < 2; ++side) {
+                                if (!(side ? f_yhi : f_ylo)) continue;
+                                const int K = side ? S.K_r[1] : S.K_l[1];
+                                const T* a = side ? S.a_r[1] : S.a_l[1];
+                                T gh[VEC];
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v) gh[v] = T(0);
+#pragma unroll 1
+                                for (int kk = 0; kk < K; ++kk) {
+                                    T val[VEC];
+                                    ld_vec<T, VEC>(colbase + ((side ? ny - K : 0) + kk) * PITCH, val);
+#pragma unroll
+                                    for (int v = 0; v < VEC; ++v) gh[v] = fma_t(a[kk], val[v], gh[v]);
+                                }
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v) gh[v] += side ? S.b_r[1] : S.b_l[1];
+                                const T* qcol = colbase + (side ? ny + 1 - TB : -1) * PITCH;   // qcol[k*PITCH] = q[k] / q[n+2-TB+k]
+                                const int kg = side ? TB - 1 : 0;
+#pragma unroll 1
+                                for (int i = 0; i < ey; ++i) {
+                                    const T* w = S.bw[1][side][i];
+                                    T res[VEC];
+#pragma unroll
+                                    for (int v = 0; v < VEC; ++v) res[v] = T(0);
+#pragma unroll 1
+                                    for (int kk = 0; kk < TB; ++kk) {
+                                        T val[VEC];
+                                        if (kk == kg) {
+#pragma unroll
+                                            for (int v = 0; v < VEC; ++v) val[v] = gh[v];
+                                        } else {
+                                            ld_vec<T, VEC>(qcol + kk * PITCH, val);
+                                        }
+                                        const T wk = w[kk];
+#pragma unroll
+                                        for (int v = 0; v < VEC; ++v) res[v] = fma_t(wk, val[v], res[v]);
+                                    }
+                                    // low: row y = i is parked R rows above its owner (local row i); high: row ny-ey+i R rows below
+                                    const int yrow = side ? (ny - ey + i) + R : i - R;
+                                    st_vec<T, VEC>(colbase + yrow * PITCH, res);
+                                }
+                            }
+                        }
+                    }
+                    // the parked values are generic-proxy writes into a slot the TMA (async proxy) overwrites later
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive_u32(fixed_u32 + 8u * slot);
+            }
+        }
+        return;
+    }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(G::REGS_COMPUTE));
+
+    // ============================================ compute warps ============================================
+    const int wy = warp;
+    int slot_a = 0, par_a = 0;                                // ring state of the next plane to acquire (continuous across items)
+    T zq[PY][VEC][NQ];
+#pragma unroll
+    for (int j = 0; j < PY; ++j)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+#pragma unroll
+            for (int t = 0; t < NQ; ++t) zq[j][v][t] = T(0);
+
+#pragma unroll 1
+    for (int q = 0;; ++q) {
+        mbar_wait_u32(item_u32 + 8u * (q % G::NIQ), (q / G::NIQ) & 1);
+        const int item = itemq[q % G::NIQ];
+        if (item < 0) break;
+        const Star2Item I = star2_item<G::TX, G::TY, MID>(L, item);
+        const int tx0 = I.tx0, ty0 = I.ty0, zc0 = I.zc0, zc1 = I.zc1;
+        const int n_planes = zc1 - zc0 + 2 * R;
+        int gx[PY], gy[PY], soff[PY];
+        bool live[PY];
+        T* ocur[PY];                                          // output pointer of each vector at the centre plane of the current step
+#pragma unroll
+        for (int j = 0; j < PY; ++j) {
+            if constexpr (MID) {
+                gx[j] = tx0 + lane * VEC;
+                gy[j] = ty0 + wy * PY + j;
+                soff[j] = (R + wy * PY + j) * PITCH + HX + lane * VEC;
+            } else {
+                const int seg = (j * NW + wy) * 32 + lane;
+                gx[j] = tx0 + seg * VEC;
+                gy[j] = 0;
+                soff[j] = HX + seg * VEC;
+            }
+            live[j] = gx[j] < nx && gy[j] < ny;
+            ocur[j] = du + (long long)gx[j] + (long long)gy[j] * S.osy + (long long)zc0 * S.osz;
+        }
+        // which of this thread's values come from the helper's evaluation (bit v: element v of the vector)
+        const bool xlo_tile = has_x && tx0 == 0, xhi_tile = has_x && tx0 + G::TX >= nx;
+        const bool ylo_tile = has_y && ty0 == 0, yhi_tile = has_y && ty0 + G::TY >= ny;
+        const bool xface = xlo_tile || xhi_tile, yface = ylo_tile || yhi_tile;
+        int xsel[PY], xoff[PY], ysel[PY];
+#pragma unroll
+        for (int j = 0; j < PY; ++j) {
+            xsel[j] = 0; xoff[j] = 0; ysel[j] = 0;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                if (xlo_tile && gx[j] + v < ex) { xsel[j] |= 1 << v; xoff[j] = -HX; }
+                if (xhi_tile && gx[j] + v >= nx - ex && gx[j] + v < nx) { xsel[j] |= 1 << v; xoff[j] = HX; }
+            }
+            if (ylo_tile && gy[j] < ey) ysel[j] = -R * PITCH;
+            if (yhi_tile && gy[j] >= ny - ey && gy[j] < ny) ysel[j] = R * PITCH;
+        }
+        // TABLE: the x-axis weights of this thread's own points stay in registers for the whole item
+        T wx[(TABLE && has_x) ? (MID ? 1 : PY) : 1][(TABLE && has_x) ? VEC : 1][(TABLE && has_x) ? NQ : 1];
+        if constexpr (TABLE && has_x) {
+#pragma unroll
+            for (int j = 0; j < (MID ? 1 : PY); ++j)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v)
+#pragma unroll
+                    for (int t = 0; t < NQ; ++t) wx[j][v][t] = __ldg(S.tab[0] + (long long)min(gx[j] + v, nx - 1) * NQ + t);
+        }
+        const T* wyp[PY];                                      // TABLE: this thread's rows of the mid-axis weight table
+        if constexpr (TABLE && has_y) {
+#pragma unroll
+            for (int j = 0; j < PY; ++j) wyp[j] = S.tab[1] + (long long)min(gy[j], ny - 1) * NQ;
+        }
+
+        // ---- priming: the first 2R planes only feed the queue (physical slots 1..2R; the first step writes slot 0) ----
+#pragma unroll
+        for (int k = 0; k < 2 * R; ++k) {
+            mbar_wait_u32(fixed_u32 + 8u * slot_a, par_a);   // landed AND its ghost-touching rows parked (implies `full`)
+            const T* pn = planes + slot_a * PLANE_ELEMS;
+#pragma unroll
+            for (int j = 0; j < PY; ++j) {
+                T val[VEC];
+                ld_vec<T, VEC>(pn + soff[j], val);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) zq[j][v][k + 1] = val[v];
+            }
+            if (k < R) {                                       // never a centre plane: free the slot now
+                __syncwarp();
+                if (lane == 0) mbar_arrive_u32(empty_u32 + 8u * slot_a);
+            }
+            if (++slot_a == NS) { slot_a = 0; par_a ^= 1; }
+        }
+        int slot_c = slot_a - R;                               // centre plane of the first step = R planes behind
+        if (slot_c < 0) slot_c += NS;
+        int z = zc0, ka = 2 * R;
+
+        // One step = acquire plane z+R, compute and store centre plane z.  ROT = u >= 0: the new plane overwrites
+        // physical queue slot u, logical tap t lives in physical slot (u + 1 + t) % NQ (NQ consecutive steps u = 0..NQ-1
+        // return to the identity layout).  ROT < 0 (EDGE): the queue is shifted instead (zq[t] = plane z-R+t) and the
+        // step carries the march-axis face logic.
+        auto step = [&](auto edge_tag, auto rot_tag) {
+            constexpr bool EDGE = decltype(edge_tag)::value;
+            constexpr int ROT = decltype(rot_tag)::value;
+            auto P = [](int t) constexpr { return ROT < 0 ? t : (ROT + 1 + t) % NQ; };
+            // --- acquire plane z+R ------------------------------------------------------------------------
+            {
+                mbar_wait_u32(fixed_u32 + 8u * slot_a, par_a);   // landed AND its ghost-touching rows parked (implies `full`)
+                const T* pn = planes + slot_a * PLANE_ELEMS;
+#pragma unroll
+                for (int j = 0; j < PY; ++j) {
+                    T val[VEC];
+                    ld_vec<T, VEC>(pn + soff[j], val);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        if constexpr (ROT < 0) {
+#pragma unroll
+                            for (int t = 0; t < NQ - 1; ++t) zq[j][v][t] = zq[j][v][t + 1];
+                            zq[j][v][NQ - 1] = val[v];
+                        } else {
+                            zq[j][v][ROT] = val[v];
+                        }
+                    }
+                }
+                if (ka >= n_planes - R) {                      // planes past the chunk only feed the queue: free the slot now
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_u32(empty_u32 + 8u * slot_a);
+                }
+            }
+            // --- centre plane z ------------------------------------------------------------------------
+            const T* pl = planes + slot_c * PLANE_ELEMS;
+            const int gz = z + S.row0_z;
+            T tot[PY][VEC];
+            // ================= x operator: window = [R halo | VEC own (already in the queue) | R halo] =================
+            if constexpr (has_x) {
+#pragma unroll
+                for (int j = 0; j < PY; ++j) {
+                    T xw[XW];
+                    load_x_halo<T, R>(pl + soff[j], xw);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) xw[R + v] = zq[j][v][P(R)];
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        T a = T(0);
+#pragma unroll
+                        for (int t = 0; t < NQ; ++t) {
+                            if constexpr (TABLE) a = fma_t(wx[MID ? 0 : j][v][t], xw[v + t], a);
+                            else a = fma_t(S.w[0][t], xw[v + t], a);
+                        }
+                        tot[j][v] = a;
+                    }
+                }
+                if (xface) {
+#pragma unroll
+                    for (int j = 0; j < PY; ++j) {
+                        if (xsel[j] != 0) {
+                            T f[VEC];
+                            ld_vec<T, VEC>(pl + soff[j] + xoff[j], f);
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) if ((xsel[j] >> v) & 1) tot[j][v] = f[v];
+                        }
+                    }
+                }
+            }
+            // ================= y operator: 2R halo rows loaded once, own rows from the queue =================
+            if constexpr (has_y) {
+                T acc[PY][VEC];
+#pragma unroll
+                for (int j = 0; j < PY; ++j)
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) acc[j][v] = T(0);
+#pragma unroll
+                for (int r = 0; r < PY + 2 * R; ++r) {
+                    T row[VEC];
+                    if (r >= R && r < R + PY) {
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) row[v] = zq[r - R][v][P(R)];
+                    } else {
+                        ld_vec<T, VEC>(pl + soff[0] + (r - R) * PITCH, row);
+                    }
+#pragma unroll
+                    for (int j = 0; j < PY; ++j) {
+                        const int t = r - j;
+                        if (t >= 0 && t < NQ) {
+                            T wyt;
+                            if constexpr (TABLE) wyt = __ldg(wyp[j] + t); else wyt = S.w[1][t];
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) acc[j][v] = fma_t(wyt, row[v], acc[j][v]);
+                        }
+                    }
+                }
+                if (yface) {
+#pragma unroll
+                    for (int j = 0; j < PY; ++j)
+                        if (ysel[j] != 0) ld_vec<T, VEC>(pl + soff[j] + ysel[j], acc[j]);   // warp-uniform: a tile row belongs to one warp
+                }
+#pragma unroll
+                for (int j = 0; j < PY; ++j)
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) tot[j][v] = has_x ? tot[j][v] + acc[j][v] : acc[j][v];
+            }
+            // ================= march-axis operator from the register queue =================
+            // rows whose stencil touches a march-axis ghost take their term from du (see below)
+            if constexpr (has_z) {
+                const bool z_low_edge = EDGE && gz < ez, z_high_edge = EDGE && gz >= S.nglob_z - ez;
+                if (!(z_low_edge || z_high_edge)) {
+                    T wz[NQ];
+#pragma unroll
+                    for (int t = 0; t < NQ; ++t) {
+                        if constexpr (TABLE) wz[t] = __ldg(S.tab[2] + (long long)gz * NQ + t); else wz[t] = S.w[2][t];
+                    }
+#pragma unroll
+                    for (int j = 0; j < PY; ++j) {
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) {
+                            T s = T(0);
+#pragma unroll
+                            for (int t = 0; t < NQ; ++t) s = fma_t(wz[t], zq[j][v][P(t)], s);
+                            tot[j][v] = (has_x || has_y) ? tot[j][v] + s : s;
+                        }
+                    }
+                } else if (z_high_edge) {                  // the term was parked in du when the queue held its planes
+#pragma unroll
+                    for (int j = 0; j < PY; ++j) {
+                        T a[VEC];
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) a[v] = T(0);
+                        if (live[j]) ld_vec<T, VEC>(ocur[j], a);
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) tot[j][v] = (has_x || has_y) ? tot[j][v] + a[v] : a[v];
+                    }
+                } else if (!(has_x || has_y)) {            // low edge row of a march-axis-only plan: its term arrives later
+#pragma unroll
+                    for (int j = 0; j < PY; ++j)
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) tot[j][v] = T(0);
+                }
+            }
+            // release the centre plane's slot, then store
+            __syncwarp();
+            if (lane == 0) mbar_arrive_u32(empty_u32 + 8u * slot_c);
+#pragma unroll
+            for (int j = 0; j < PY; ++j)
+                if (live[j]) st_vec<T, VEC>(ocur[j], tot[j]);
+
+            if constexpr (has_z && EDGE) {
+                // --- march-axis rows that touch a ghost, from the register queue -------------------------------
+                // low rows r < ez need q[0..TB-1] = ghost, planes 0..2R: exactly the queue when the centre is global plane R.
+                // Their x/y part is already in du (stored above at the steps gz = r); add the march-axis term now (it is
+                // the last operator, so the association matches the reference's sum).
+                if (gz == R && ez > 0) {
+#pragma unroll
+                    for (int j = 0; j < PY; ++j) {
+                        if (!live[j]) continue;
+                        T gl[VEC];
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) {
+                            T s = T(0);
+#pragma unroll
+                            for (int m = 0; m < NQ; ++m) s = fma_t(S.azl_pad[m], zq[j][v][m], s);
+                            gl[v] = s + S.b_l[2];
+                        }
+#pragma unroll 1
+                        for (int r = 0; r < ez; ++r) {
+                            T* dst = ocur[j] + (long long)(r - S.row0_z - z) * S.osz;
+                            T old[VEC];
+                            ld_vec<T, VEC>(dst, old);
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) {
+                                T s = fma_t(S.bw[2][0][r][0], gl[v], T(0));
+#pragma unroll
+                                for (int kk = 1; kk < TB; ++kk) s = fma_t(S.bw[2][0][r][kk], zq[j][v][kk - 1], s);
+                                old[v] = old[v] + s;
+                            }
+                            st_vec<T, VEC>(dst, old);
+                        }
+                    }
+                }
+                // high rows need planes n-1-2R..n-1 and the high ghost: the queue when the centre is global plane n-1-R.
+                // Their term is parked in du now and picked up (tot + du) when those rows are computed a few steps later.
+                if (gz == S.nglob_z - 1 - R && ez > 0) {
+#pragma unroll
+                    for (int j = 0; j < PY; ++j) {
+                        if (!live[j]) continue;
+                        T gh[VEC];
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) {
+                            T s = T(0);
+#pragma unroll
+                            for (int m = 0; m < NQ; ++m) s = fma_t(S.azr_pad[m], zq[j][v][m], s);
+                            gh[v] = s + S.b_r[2];
+                        }
+#pragma unroll 1
+                        for (int r = 0; r < ez; ++r) {
+                            T* dst = ocur[j] + (long long)(S.nglob_z - ez + r - S.row0_z - z) * S.osz;
+                            T out[VEC];
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) {
+                                T s = T(0);
+#pragma unroll
+                                for (int kk = 0; kk < TB - 1; ++kk) s = fma_t(S.bw[2][1][r][kk], zq[j][v][kk], s);
+                                out[v] = fma_t(S.bw[2][1][r][TB - 1], gh[v], s);
+                            }
+                            st_vec<T, VEC>(dst, out);
+                        }
+                    }
+                }
+            }
+            // --- advance the ring and the output pointers ---------------------------------------------------
+            ++z; ++ka;
+            if (++slot_a == NS) { slot_a = 0; par_a ^= 1; }
+            if (++slot_c == NS) slot_c = 0;
+#pragma unroll
+            for (int j = 0; j < PY; ++j) ocur[j] += S.osz;
+        };
+
+        // Step ranges of this item: [zc0, z_lo) edge steps next to the low march-axis face (global planes 0..R),
+        // [z_lo, z_rot) rotated steps, [z_rot, zc1) edge steps up to the high march-axis face.  The rotated run before
+        // edge steps is a whole number of rotations, so that the queue is back in the identity layout.
+        int z_lo = zc0, z_rot = zc1;
+        if constexpr (has_z) {
+            z_lo = max(zc0, min(zc1, R + 1 - S.row0_z));
+            const int z_hi = min(zc1, max(z_lo, S.nglob_z - 1 - R - S.row0_z));
+            z_rot = z_hi == zc1 ? zc1 : z_lo + ((z_hi - z_lo) / NQ) * NQ;
+        }
+        using Shift = std::integral_constant<int, -1>;
+#pragma unroll 1
+        while (z < z_lo) step(std::true_type{}, Shift{});
+        if (z < z_rot) {
+            auto at_end = [&]() { return z == z_rot; };
+#pragma unroll 1
+            while (!rot_steps<NQ>(step, at_end)) {}
+        }
+#pragma unroll 1
+        while (z < zc1) step(std::true_type{}, Shift{});
+    }
+}
+
+struct Star2Runtime {            // per process and device: the mapped error word of the in-kernel halo wait, the scheduler words
+    int* err_host = nullptr;
+    int* err_dev = nullptr;
+    unsigned int* sched = nullptr;   // device memory, 2 words, zero between launches
+};
+Star2Runtime& star2_rt();
+
+template <typename T, int R, bool MID, int MASK, bool TABLE>
+int32_t launch_variant2(const StarConfig& C, const void* u, void* du, long long z0, long long z1, cudaStream_t s) {
+    using G = Star2Geom<T, R, MID>;
+    const StarParams<T, R>& S = *reinterpret_cast<const StarParams<T, R>*>(C.params.data());
+    auto kern = k_star2<T, R, MID, MASK, TABLE>;
+    static int attr_device = -1;
+    int dev = 0;
+    DEO_CUDA(cudaGetDevice(&dev));
+    if (attr_device != dev) {
+        DEO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
+        attr_device = dev;
+    }
+    const long long len = z1 - z0;
+    const long long tiles_x = (S.nx + G::TX - 1) / G::TX;
+    const long long tiles = tiles_x * (MID ? (S.ny + G::TY - 1) / G::TY : 1);
+    // Chunking of the march axis: among the chunk lengths <= zchunk_max pick the one with the shortest makespan in
+    // plane-steps (one CTA per SM works through ceil(items / SMs) items, each costing its planes plus 2R priming
+    // planes); never cut a face's one-sided rows.
+    long long zmax = C.zchunk_max > 0 ? C.zchunk_max : len;
+    if (zmax < 4 * R + 4) zmax = 4 * R + 4;
+    long long zc = len;
+    {
+        double best = 1e30;
+        const long long slots = C.sm_count;
+        for (long long nch = (len + zmax - 1) / zmax; nch <= len; ++nch) {
+            const long long c = (len + nch - 1) / nch;
+            if (c < 4 * R + 4 && nch > 1) break;
+            const long long nchunks = (len + c - 1) / c;
+            const long long last = len - (nchunks - 1) * c;
+            if (nchunks > 1 && last < R + 1) continue;
+            const long long rounds = (tiles * nchunks + slots - 1) / slots;
+            const double cost = (double)rounds * (double)(c + 2 * R);
+            if (cost < best - 1e-12) { best = cost; zc = c; }
+            if (c * 2 < zmax) break;                       // do not go below half the bound
+        }
+    }
+    Star2Launch Lp{};
+    Lp.z_begin = (int)z0; Lp.z_end = (int)z1; Lp.zchunk = (int)zc;
+    Lp.nchunks = (int)((len + zc - 1) / zc);
+    Lp.tiles_x = (int)tiles_x; Lp.tiles_xy = (int)tiles;
+    DEO_REQUIRE(tiles * Lp.nchunks < (1LL << 31), "star kernel: too many work items");
+    Lp.n_items = (int)(tiles * Lp.nchunks);
+    const bool fused = C.halo_flag != nullptr;
+    if (fused && Lp.nchunks < 3) { set_error("star kernel: fused halo launch needs at least 3 chunks"); return DEO_ERR_UNSUPPORTED; }
+    Lp.fused = fused ? 1 : 0;
+    Lp.halo_flag = fused ? C.halo_flag : nullptr;
+    Lp.halo_expect = C.halo_expect; Lp.halo_sides = C.halo_sides;
+    Lp.err_word = star2_rt().err_dev;
+    Lp.sched = star2_rt().sched;
+    DEO_REQUIRE(Lp.sched != nullptr, "star kernel: scheduler words could not be allocated");
+    Lp.timeout_ns = C.halo_timeout_ns;
+    Lp.accumulate = 0; Lp.axpy = 0; Lp.dt = 0.0;
+    const unsigned grid = (unsigned)(Lp.n_items < C.sm_count ? Lp.n_items : C.sm_count);
+    kern<<<grid, G::THREADS, G::SMEM, s>>>(C.tmap, S, Lp, (const T*)u, (T*)du);
+    DEO_CUDA(cudaGetLastError());
+    return DEO_OK;
+}
+
+template <typename T, int R>
+int32_t star2_launch_R(const StarConfig& C, const void* u, void* du, long long z0, long long z1, cudaStream_t s);
+
+template <typename T, int R, bool MID, bool TABLE>
+int32_t star2_launch_mask(const StarConfig& C, const void* u, void* du, long long z0, long long z1, cudaStream_t s) {
+    switch (C.mask) {
+        case 1: return launch_variant2<T, R, MID, 1, TABLE>(C, u, du, z0, z1, s);
+        case 4: return launch_variant2<T, R, MID, 4, TABLE>(C, u, du, z0, z1, s);
+        case 5: return launch_variant2<T, R, MID, 5, TABLE>(C, u, du, z0, z1, s);
+    }
+    if constexpr (MID) {
+        switch (C.mask) {
+            case 2: return launch_variant2<T, R, MID, 2, TABLE>(C, u, du, z0, z1, s);
+            case 3: return launch_variant2<T, R, MID, 3, TABLE>(C, u, du, z0, z1, s);
+            case 6: return launch_variant2<T, R, MID, 6, TABLE>(C, u, du, z0, z1, s);
+            case 7: return launch_variant2<T, R, MID, 7, TABLE>(C, u, du, z0, z1, s);
+        }
+    }
+    set_error("star kernel: unsupported operator mask %d", C.mask);
+    return DEO_ERR_UNSUPPORTED;
+}
+
+#define DEO_STAR2_INSTANTIATE(R_)                                                                                             \
+    template <typename T, int R>                                                                                              \
+    int32_t star2_launch_R(const StarConfig& C, const void* u, void* du, long long z0, long long z1, cudaStream_t s) {       \
+        if (C.table) return C.mid ? star2_launch_mask<T, R, true, true>(C, u, du, z0, z1, s)                                 \
+                                  : star2_launch_mask<T, R, false, true>(C, u, du, z0, z1, s);                               \
+        return C.mid ? star2_launch_mask<T, R, true, false>(C, u, du, z0, z1, s)                                             \
+                     : star2_launch_mask<T, R, false, false>(C, u, du, z0, z1, s);                                           \
+    }                                                                                                                          \
+    template int32_t star2_launch_R<double, R_>(const StarConfig&, const void*, void*, long long, long long, cudaStream_t);   \
+    template int32_t star2_launch_R<float, R_>(const StarConfig&, const void*, void*, long long, long long, cudaStream_t);
+
+}  // namespace deo

@@ -82,11 +82,21 @@ int32_t deo_init(int32_t device) {
     return DEO_OK;
 }
 
+// A slab launch that gave up waiting for its neighbours' halo planes raises a mapped host word instead of trapping
+// (the context stays usable); the next synchronising call reports it once.
+static int32_t check_halo_timeout() {
+    if (star_take_halo_timeout()) {
+        set_error("halo exchange timed out: a slab launch waited longer than the bound (DEO_HALO_TIMEOUT_S) for a neighbour's halo planes; its result is invalid");
+        return DEO_ERR_CUDA;
+    }
+    return DEO_OK;
+}
+
 int32_t deo_sync(void) {
     if (!rt().ready) return DEO_OK;
     DEO_CUDA(cudaStreamSynchronize(rt().stream));
     DEO_CUDA(cudaStreamSynchronize(rt().comm_stream));
-    return DEO_OK;
+    return check_halo_timeout();
 }
 
 int32_t deo_last_error(char* buf, size_t len) {
@@ -173,7 +183,7 @@ int32_t deo_buffer_download(void* host, const deo_buffer* src, size_t bytes) {
     DEO_REQUIRE(bytes <= src->bytes, "deo_buffer_download: %zu bytes from a %zu-byte buffer", bytes, src->bytes);
     DEO_CUDA(cudaMemcpyAsync(host, src->ptr, bytes, cudaMemcpyDeviceToHost, rt().stream));
     DEO_CUDA(cudaStreamSynchronize(rt().stream));
-    return DEO_OK;
+    return check_halo_timeout();
 }
 
 int32_t deo_buffer_devptr(const deo_buffer* buf, void** devptr) {

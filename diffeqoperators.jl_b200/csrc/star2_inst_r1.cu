@@ -1,0 +1,6 @@
+// Instantiates the persistent tiled kernel for stencil radius 1 (Float32 and Float64, 3-D tile and 2-D strip).
+#include "kernel_star2.cuh"
+
+namespace deo {
+DEO_STAR2_INSTANTIATE(1)
+}  // namespace deo

@@ -21,7 +21,7 @@ u = D.DeviceArray.from_host(host.reshape(shape, order="F"))
 du = D.DeviceArray(shape, dtype)
 del host, blk
 for cfg in configs:
-    for k in ("DEO_TMA_L2PROMO", "DEO_STAR_ZCHUNK", "DEO_STAR_PY", "DEO_STAR_NWY"):
+    for k in ("DEO_TMA_L2PROMO", "DEO_STAR_ZCHUNK", "DEO_STAR_PY", "DEO_STAR_NWY", "DEO_STAR_V"):
         os.environ.pop(k, None)
     os.environ.update(cfg)
     A = D.CenteredDifference[1](2, a, h[0], shape[0], dtype=dtype)
