@@ -323,10 +323,13 @@ int32_t star_configure(deo_plan* plan) {
     const char* env_nwy = getenv("DEO_STAR_NWY");
     cfg->nwy = (env_nwy && atoi(env_nwy) == 16 && cfg->py == 2) ? 16 : 8;
     cfg->zchunk_pref = 64;
-    cfg->zchunk_max = getenv("DEO_STAR_ZCHUNK") ? atoi(getenv("DEO_STAR_ZCHUNK")) : 32;
+    cfg->v2 = !(getenv("DEO_STAR_V") && atoi(getenv("DEO_STAR_V")) == 1);            // A/B: DEO_STAR_V=1 selects the first-generation kernel
+    // march-axis chunk bound: short items re-synchronise the CTAs often (L2 reuse of the shared halo rows) at the price of
+    // 2R priming planes each; measured best: 24 planes (3-D) / 16 rows (2-D strips) for the persistent kernel, 32 for the first one
+    cfg->zchunk_max = getenv("DEO_STAR_ZCHUNK") ? atoi(getenv("DEO_STAR_ZCHUNK")) : (cfg->v2 ? (mid ? 24 : 16) : 32);
+    if (cfg->zchunk_max < 1) cfg->zchunk_max = cfg->v2 ? 24 : 32;
     cfg->l2promo = getenv("DEO_TMA_L2PROMO") ? atoi(getenv("DEO_TMA_L2PROMO")) : 3;
     cfg->group = getenv("DEO_STAR_GROUP") ? atoi(getenv("DEO_STAR_GROUP")) : -1;   // measured: the plain order is fastest
-    cfg->v2 = !(getenv("DEO_STAR_V") && atoi(getenv("DEO_STAR_V")) == 1);            // A/B: DEO_STAR_V=1 selects the first-generation kernel
     if (getenv("DEO_HALO_TIMEOUT_S") && atof(getenv("DEO_HALO_TIMEOUT_S")) > 0)
         cfg->halo_timeout_ns = (unsigned long long)(atof(getenv("DEO_HALO_TIMEOUT_S")) * 1e9);
 

@@ -25,10 +25,16 @@ namespace deo {
 struct Star2Launch {
     int z_begin, z_end, zchunk, nchunks;
     int tiles_x, tiles_xy, n_items, fused;
+    int band;                        // tiles per band (a multiple of tiles_x; tiles_xy when the whole layer is one band)
     const int* halo_flag;            // slab plans: [0] low side, [1] high side, written over NVLink after the halo planes
     int halo_expect, halo_sides;
     int* err_word;                   // mapped host word: set when the halo wait expires (the host turns it into DEO_ERR_CUDA)
     unsigned long long timeout_ns;
+    int stagger_ns;                  // experiment: CTA b starts b * stagger_ns late
+    int pace_cycles;                 // experiment: minimum SM cycles between two plane issues of a CTA
+    int ns;                          // ring slots in use
+    int st_cs, ld_policy;            // cache hints: streaming stores of du; TMA loads of u with L2 evict_last (1) / evict_first (2)
+    unsigned long long* trace;       // debug (DEO_STAR2_TRACE): per item {first plane issued (ns), last plane issued (ns), SM id}
     unsigned int* sched;             // [0] next work item (dynamic scheduling), [1] CTAs finished; both return to 0 at the end of a launch
     int accumulate, axpy;            // du += result (overwrite = false);  du = u + dt * result
     double dt;
@@ -47,18 +53,23 @@ struct Star2Geom {
     static constexpr int NBOX = MID ? 1 : (PITCH + BOXW - 1) / BOXW;
     static constexpr int PLANE = MID ? PITCH * ROWS : NBOX * BOXW;   // elements written per plane
     static constexpr int PLANE_BYTES = ((PLANE * (int)sizeof(T) + 127) / 128) * 128;
-    static constexpr int NS_FIT = (216 * 1024) / PLANE_BYTES;
-    static constexpr int NS_CAP = R + 12;
+    static constexpr int TAB_ZMAX = 64;                           // TABLE variants: march-axis rows staged per item (chunk bound)
+    // one staging buffer: [TY][NQ] mid-axis rows + [TAB_ZMAX][NQ] march-axis rows + (3-D) [NQ][TX] x-axis rows
+    static constexpr int TAB_ELEMS = (TY + TAB_ZMAX + (MID ? TX : 0)) * (2 * R + 1);
+    static constexpr int NS_FIT = (216 * 1024 - 2 * TAB_ELEMS * (int)sizeof(T)) / PLANE_BYTES;
+    static constexpr int NS_CAP = R + 8;
     static constexpr int NS = NS_FIT < NS_CAP ? NS_FIT : NS_CAP;
     static constexpr int NQ = 2 * R + 1;
     static constexpr int THREADS = (NW + 4) * 32;                 // 4 compute warpgroups + 1 helper warpgroup (producer + 3 evaluators)
     // Register split (setmaxnreg).  The launch allocates 640 * 96 registers to the CTA; setmaxnreg.inc can only draw on
-    // what setmaxnreg.dec returned to that per-CTA pool: the helper warpgroup gives back 128 * (96 - 32) = 8192, the four
-    // compute warpgroups take 512 * (112 - 96) = 8192.
-    static constexpr int REGS_COMPUTE = 112, REGS_HELPER = 32;
+    // what setmaxnreg.dec returned to that per-CTA pool: the helper warpgroup gives back 128 * (96 - 56) = 5120, the four
+    // compute warpgroups take 512 * (104 - 96) = 4096.
+    static constexpr int REGS_COMPUTE = 104, REGS_HELPER = 56;
     static_assert(512 * (REGS_COMPUTE - 96) <= 128 * (96 - REGS_HELPER), "setmaxnreg: the per-CTA register pool would run dry (deadlock)");
     static constexpr int NIQ = 8;                                 // item queue entries (the producer is never more than 3 items ahead)
-    static constexpr size_t SMEM = (size_t)NS * PLANE_BYTES + (3 * NS + NIQ) * sizeof(uint64_t) + NIQ * sizeof(int) + 64;
+    static constexpr size_t TAB_OFF = (((size_t)NS * PLANE_BYTES + (3 * NS + NIQ) * sizeof(uint64_t) + NIQ * sizeof(int) + 15) / 16) * 16;
+    static constexpr size_t SMEM = TAB_OFF + 16;
+    static constexpr size_t SMEM_TABLE = TAB_OFF + 2 * (size_t)TAB_ELEMS * sizeof(T) + 16;   // + double-buffered weight rows of the current item
     static_assert(NS >= R + 4, "ring too small");
 };
 
@@ -78,6 +89,20 @@ __device__ __forceinline__ unsigned long long global_ns() {
     return t;
 }
 
+// 16-byte store with the streaming (evict-first) hint: du is written once and never read back by this kernel, so it should
+// not displace the u lines the neighbouring tiles still have to read from L2
+template <typename T, int N>
+__device__ __forceinline__ void st_vec_cs(T* p, const T (&in)[N]) {
+    if constexpr (N == 2) asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(in[0]), "d"(in[1]) : "memory");
+    else asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(in[0]), "f"(in[1]), "f"(in[2]), "f"(in[3]) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_hint(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+        : "memory");
+}
+
 // f(false_type, integral_constant<int, U>) for U = 0 .. N-1, leaving early (returns true) as soon as stop() holds
 template <int N, int U = 0, class F, class Stop>
 __device__ __forceinline__ bool rot_steps(F& f, Stop& stop) {
@@ -92,10 +117,22 @@ __device__ __forceinline__ bool rot_steps(F& f, Stop& stop) {
 // rows / columns two tiles share are still in L2 when the second one asks.  Slab launches that wait for their halo
 // planes in the kernel schedule the first and the last chunk last.
 struct Star2Item { int tx0, ty0, zc0, zc1; };
+// Item order.  The x-y tiles are grouped into BANDS of about one grid's worth of tiles (whole tile rows); inside a band the
+// list runs chunk-major: every tile of the band for chunk 0, the same tiles for chunk 1, ...  Two kinds of reuse follow:
+// the CTAs of the grid work on neighbouring tiles of the same chunk at the same time (shared halo rows / columns hit in
+// L2), and a tile's next chunk is taken up right when its previous chunk ends, so its 2R priming planes -- the planes the
+// previous chunk read last -- are still in L2 too.  Plain chunk-major order over a layer larger than the grid loses the
+// second kind (the next chunk of a tile starts several item-times later).
 template <int TX, int TY, bool MID>
 __device__ __forceinline__ Star2Item star2_item(const Star2Launch& L, int it) {
-    int chunk = it / L.tiles_xy;
-    const int tile = it - chunk * L.tiles_xy;
+    const int per_band = L.band * L.nchunks;
+    const int b = it / per_band;
+    const int first = b * L.band;                                  // first tile of the band
+    const int bt = min(L.band, L.tiles_xy - first);                 // tiles in this band (the last one may be short)
+    const int r = it - b * per_band;
+    int chunk = r / bt;
+    const int tile = first + (r - chunk * bt);
+    // slab launches that wait for their halo planes in the kernel schedule the first and the last chunk last (one band)
     if (L.fused) chunk = chunk < L.nchunks - 2 ? chunk + 1 : (chunk == L.nchunks - 2 ? 0 : L.nchunks - 1);
     Star2Item I;
     I.tx0 = (tile % L.tiles_x) * TX;
@@ -103,6 +140,90 @@ __device__ __forceinline__ Star2Item star2_item(const Star2Launch& L, int it) {
     I.zc0 = L.z_begin + chunk * L.zchunk;
     I.zc1 = min(I.zc0 + L.zchunk, L.z_end);
     return I;
+}
+
+// ---- evaluation of the x / y rows whose stencil touches a ghost, straight from a landed shared-memory plane --------------
+// (helper warps).  SIDE 0 = low face, 1 = high face (compile time: the weights are direct constant-bank operands).  Sums run
+// over the taps in ascending q order, exactly like the per-point kernel (bitwise equal results).
+//
+// x: lane <-> tile row.  The value of x = i (low) is parked HX columns to the left of its owner, i.e. in local column i;
+//    the value of x = nx-ex+i (high) HX columns to the right of its owner.  Those cells hold nothing but the TMA's
+//    out-of-bounds zeros on a face tile.
+template <typename T, int R, bool MID, int SIDE>
+__device__ __forceinline__ void star2_fix_x(const StarParams<T, R>& S, T* pl, int tx0, int ty0, int nx, int ny, int ex, int lane) {
+    using G = Star2Geom<T, R, MID>;
+    constexpr int TB = 2 * R + 2, HX = G::HX, PITCH = G::PITCH;
+#pragma unroll 1
+    for (int rr = lane; rr < G::TY; rr += 32) {
+        if (MID && ty0 + rr >= ny) continue;
+        T* rowl = pl + (MID ? (R + rr) * PITCH : 0);      // local row
+        const T* row = rowl + HX - tx0;                  // row[x] = value at global x
+        const int K = SIDE ? S.K_r[0] : S.K_l[0];
+        const T* a = SIDE ? S.a_r[0] : S.a_l[0];
+        const T* arow = row + (SIDE ? nx - K : 0);
+        T gh = T(0);
+#pragma unroll 1
+        for (int kk = 0; kk < K; ++kk) gh = fma_t(a[kk], arow[kk], gh);
+        gh += SIDE ? S.b_r[0] : S.b_l[0];
+        const T* qrow = SIDE ? row + (nx + 1 - TB) : row - 1;   // qrow[k] = q[k] (low) / q[n+2-TB+k] (high)
+        T q[TB];
+#pragma unroll
+        for (int kk = 0; kk < TB; ++kk) q[kk] = (kk == (SIDE ? TB - 1 : 0)) ? gh : qrow[kk];
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            if (i < ex) {
+                T res = T(0);
+#pragma unroll
+                for (int kk = 0; kk < TB; ++kk) res = fma_t(S.bw[0][SIDE][i][kk], q[kk], res);
+                if (!SIDE) rowl[i] = res;
+                else rowl[(nx - ex + i) - tx0 + 2 * HX] = res;
+            }
+        }
+    }
+}
+// y: lane <-> one 16-byte vector of columns (conflict-free vector loads).  Row y = i (low) is parked R rows above its owner,
+//    i.e. in local row i; row ny-ey+i (high) R rows below its owner.
+template <typename T, int R, int SIDE>
+__device__ __forceinline__ void star2_fix_y(const StarParams<T, R>& S, T* pl, int ty0, int ny, int ey, int lane) {
+    using G = Star2Geom<T, R, true>;
+    constexpr int TB = 2 * R + 2, HX = G::HX, PITCH = G::PITCH, VEC = G::VEC;
+    T* colbase = pl + (R - ty0) * PITCH + HX + lane * VEC;      // colbase[y*PITCH + v] = value at global row y
+    const int K = SIDE ? S.K_r[1] : S.K_l[1];
+    const T* a = SIDE ? S.a_r[1] : S.a_l[1];
+    T gh[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) gh[v] = T(0);
+#pragma unroll 1
+    for (int kk = 0; kk < K; ++kk) {
+        T val[VEC];
+        ld_vec<T, VEC>(colbase + ((SIDE ? ny - K : 0) + kk) * PITCH, val);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) gh[v] = fma_t(a[kk], val[v], gh[v]);
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) gh[v] += SIDE ? S.b_r[1] : S.b_l[1];
+    const T* qcol = colbase + (SIDE ? ny + 1 - TB : -1) * PITCH;   // qcol[k*PITCH] = q[k] / q[n+2-TB+k]
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        if (i < ey) {
+            T res[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) res[v] = T(0);
+#pragma unroll
+            for (int kk = 0; kk < TB; ++kk) {
+                T val[VEC];
+                if (kk == (SIDE ? TB - 1 : 0)) {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) val[v] = gh[v];
+                } else {
+                    ld_vec<T, VEC>(qcol + kk * PITCH, val);
+                }
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) res[v] = fma_t(S.bw[1][SIDE][i][kk], val[v], res[v]);
+            }
+            st_vec<T, VEC>(colbase + (SIDE ? (ny - ey + i) + R : i - R) * PITCH, res);
+        }
+    }
 }
 
 template <typename T, int R, bool MID, int MASK, bool TABLE>
@@ -123,6 +244,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
     uint64_t* const fixedb = empty + NS;
     uint64_t* const itemb = fixedb + NS;                       // item queue: entry q % NIQ is valid once phase q / NIQ of its barrier completes
     volatile int* const itemq = reinterpret_cast<volatile int*>(itemb + G::NIQ);
+    T* const tabbuf = reinterpret_cast<T*>(smem_raw + G::TAB_OFF);   // TABLE only (inside SMEM_TABLE)
     const uint32_t full_u32 = smem_u32(full), empty_u32 = smem_u32(empty), fixed_u32 = smem_u32(fixedb), item_u32 = smem_u32(itemb);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -132,6 +254,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    const int ns = L.ns;                                      // ring slots in use (<= NS): the TMA prefetch depth is ns - R - 1 planes
     const int nx = S.nx, ny = S.ny;
     const int ex = S.nedge[0], ey = S.nedge[1], ez = S.nedge[2];
 
@@ -147,6 +270,14 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
             // The producer publishes each item to the other warps through the item queue.
             int g = 0, q = 0;
             int item = blockIdx.x;
+            uint64_t policy = 0;
+            long long t_issue = clock64();
+            if (L.ld_policy == 1) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+            if (L.ld_policy == 2) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+            if (L.stagger_ns > 0) {
+                const unsigned long long t0 = global_ns(), dt = (unsigned long long)L.stagger_ns * blockIdx.x;
+                while (global_ns() - t0 < dt) __nanosleep(100);
+            }
 #pragma unroll 1
             for (;;) {
                 const bool last = item >= L.n_items;
@@ -155,6 +286,12 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                 ++q;
                 if (last) break;
                 const int next = (int)gridDim.x + (int)atomicAdd(L.sched, 1u);   // fetched one item ahead: its latency hides behind this item's planes
+                if (L.trace) {
+                    unsigned smid;
+                    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                    L.trace[3 * item] = global_ns();
+                    L.trace[3 * item + 2] = smid;
+                }
                 const Star2Item I = star2_item<G::TX, G::TY, MID>(L, item);
                 const int n = I.zc1 - I.zc0 + 2 * R;
                 if (L.halo_flag != nullptr) {
@@ -180,19 +317,25 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                 }
 #pragma unroll 1
                 for (int k = 0; k < n; ++k, ++g) {
-                    const int slot = g % NS;
-                    if (g >= NS) mbar_wait_u32(empty_u32 + 8u * slot, ((g / NS) - 1) & 1);
+                    const int slot = g % ns;
+                    if (g >= ns) mbar_wait_u32(empty_u32 + 8u * slot, ((g / ns) - 1) & 1);
+                    if (L.pace_cycles > 0) {
+                        while (clock64() - t_issue < (long long)L.pace_cycles) {}
+                        t_issue = clock64();
+                    }
                     mbar_expect_tx(&full[slot], (uint32_t)(G::PLANE * sizeof(T)));
                     const int pz = I.zc0 - R + k + S.in_off_z;
                     T* dst = planes + (size_t)slot * PLANE_ELEMS;
                     if constexpr (MID) {
-                        tma_load_3d(dst, &tmap, &full[slot], I.tx0 - HX, I.ty0 - R, pz);
+                        if (L.ld_policy) tma_load_3d_hint(dst, &tmap, &full[slot], I.tx0 - HX, I.ty0 - R, pz, policy);
+                        else tma_load_3d(dst, &tmap, &full[slot], I.tx0 - HX, I.ty0 - R, pz);
                     } else {
 #pragma unroll
                         for (int b = 0; b < G::NBOX; ++b)
                             tma_load_3d(dst + b * G::BOXW, &tmap, &full[slot], I.tx0 - HX + b * G::BOXW, 0, pz);
                     }
                 }
+                if (L.trace) L.trace[3 * item + 1] = global_ns();
                 item = next;
             }
             // the last CTA to get here puts the scheduler words back to zero for the next launch (launches on a stream do
@@ -216,101 +359,23 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
             const bool face = f_xlo || f_xhi || f_ylo || f_yhi;
 #pragma unroll 1
             for (int k = 0; k < n; ++k, ++g) {
-                const int slot = g % NS;
+                const int slot = g % ns;
                 // a ring slot always belongs to the same evaluator: a waiter must see EVERY phase of a barrier, in order
                 // (TMA planes can land out of order; waiting for phase m while m-1 is still open returns at once)
                 if (slot % 3 != me) continue;
                 // Chain per slot use: TMA lands (`full`) -> this warp parks the ghost-touching rows and arrives on `fixed` ->
                 // the compute warps acquire (they wait on `fixed` only) ... release (`empty`) -> the producer refills.
                 // Every use gets exactly one arrival on each barrier, so no waiter can be lapped by two phases.
-                mbar_wait_u32(full_u32 + 8u * slot, (g / NS) & 1);
+                mbar_wait_u32(full_u32 + 8u * slot, (g / ns) & 1);
                 if (face && k >= R && k < n - R) {             // only planes that become a centre plane are read by the x / y parts
                     T* pl = planes + (size_t)slot * PLANE_ELEMS;
-                    // Register-lean on purpose (this warpgroup runs on 32 registers per thread, see REGS_HELPER): every tap is
-                    // re-read from shared memory instead of being kept in a register window.
                     if constexpr (has_x) {
-                        // lane <-> tile row; (side, edge row i) uniform: weights come from the constant bank
-                        if (f_xlo || f_xhi) {
-#pragma unroll 1
-                            for (int rr = lane; rr < G::TY; rr += 32) {
-                                if (MID && I.ty0 + rr >= ny) continue;
-                                T* rowl = pl + (MID ? (R + rr) * PITCH : 0);      // local row
-                                const T* row = rowl + HX - I.tx0;                // row[x] = value at global x
-#pragma unroll 1
-                                for (int side = 0; side < 2; ++side) {
-                                    if (!(side ? f_xhi : f_xlo)) continue;
-                                    const int K = side ? S.K_r[0] : S.K_l[0];
-                                    const T* a = side ? S.a_r[0] : S.a_l[0];
-                                    const T* arow = row + (side ? nx - K : 0);
-                                    T gh = T(0);
-#pragma unroll 1
-                                    for (int kk = 0; kk < K; ++kk) gh = fma_t(a[kk], arow[kk], gh);
-                                    gh += side ? S.b_r[0] : S.b_l[0];
-                                    const T* qrow = side ? row + (nx + 1 - TB) : row - 1;   // qrow[k] = q[k] (low) / q[n+2-TB+k] (high)
-                                    const int kg = side ? TB - 1 : 0;                       // the tap that is the ghost
-#pragma unroll 1
-                                    for (int i = 0; i < ex; ++i) {
-                                        const T* w = S.bw[0][side][i];
-                                        T res = T(0);
-#pragma unroll 1
-                                        for (int kk = 0; kk < TB; ++kk) res = fma_t(w[kk], kk == kg ? gh : qrow[kk], res);
-                                        // low: the value of x = i is parked HX columns to the left of its owner (local column i);
-                                        // high: the value of x = nx-ex+i HX columns to the right of its owner
-                                        if (!side) rowl[i] = res;
-                                        else rowl[(nx - ex + i) - I.tx0 + 2 * HX] = res;
-                                    }
-                                }
-                            }
-                        }
+                        if (f_xlo) star2_fix_x<T, R, MID, 0>(S, pl, I.tx0, I.ty0, nx, ny, ex, lane);
+                        if (f_xhi) star2_fix_x<T, R, MID, 1>(S, pl, I.tx0, I.ty0, nx, ny, ex, lane);
                     }
                     if constexpr (has_y) {
-                        // lane <-> one 16-byte vector of columns: conflict-free vector loads
-                        if (f_ylo || f_yhi) {
-                            T* colbase = pl + (R - I.ty0) * PITCH + HX + lane * VEC;      // colbase[y*PITCH + v] = value at global row y
-#pragma unroll 1
-                            for (int side = 0; side < 2; ++side) {
-                                if (!(side ? f_yhi : f_ylo)) continue;
-                                const int K = side ? S.K_r[1] : S.K_l[1];
-                                const T* a = side ? S.a_r[1] : S.a_l[1];
-                                T gh[VEC];
-#pragma unroll
-                                for (int v = 0; v < VEC; ++v) gh[v] = T(0);
-#pragma unroll 1
-                                for (int kk = 0; kk < K; ++kk) {
-                                    T val[VEC];
-                                    ld_vec<T, VEC>(colbase + ((side ? ny - K : 0) + kk) * PITCH, val);
-#pragma unroll
-                                    for (int v = 0; v < VEC; ++v) gh[v] = fma_t(a[kk], val[v], gh[v]);
-                                }
-#pragma unroll
-                                for (int v = 0; v < VEC; ++v) gh[v] += side ? S.b_r[1] : S.b_l[1];
-                                const T* qcol = colbase + (side ? ny + 1 - TB : -1) * PITCH;   // qcol[k*PITCH] = q[k] / q[n+2-TB+k]
-                                const int kg = side ? TB - 1 : 0;
-#pragma unroll 1
-                                for (int i = 0; i < ey; ++i) {
-                                    const T* w = S.bw[1][side][i];
-                                    T res[VEC];
-#pragma unroll
-                                    for (int v = 0; v < VEC; ++v) res[v] = T(0);
-#pragma unroll 1
-                                    for (int kk = 0; kk < TB; ++kk) {
-                                        T val[VEC];
-                                        if (kk == kg) {
-#pragma unroll
-                                            for (int v = 0; v < VEC; ++v) val[v] = gh[v];
-                                        } else {
-                                            ld_vec<T, VEC>(qcol + kk * PITCH, val);
-                                        }
-                                        const T wk = w[kk];
-#pragma unroll
-                                        for (int v = 0; v < VEC; ++v) res[v] = fma_t(wk, val[v], res[v]);
-                                    }
-                                    // low: row y = i is parked R rows above its owner (local row i); high: row ny-ey+i R rows below
-                                    const int yrow = side ? (ny - ey + i) + R : i - R;
-                                    st_vec<T, VEC>(colbase + yrow * PITCH, res);
-                                }
-                            }
-                        }
+                        if (f_ylo) star2_fix_y<T, R, 0>(S, pl, I.ty0, ny, ey, lane);
+                        if (f_yhi) star2_fix_y<T, R, 1>(S, pl, I.ty0, ny, ey, lane);
                     }
                     // the parked values are generic-proxy writes into a slot the TMA (async proxy) overwrites later
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -376,20 +441,38 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
             if (ylo_tile && gy[j] < ey) ysel[j] = -R * PITCH;
             if (yhi_tile && gy[j] >= ny - ey && gy[j] < ny) ysel[j] = R * PITCH;
         }
-        // TABLE: the x-axis weights of this thread's own points stay in registers for the whole item
-        T wx[(TABLE && has_x) ? (MID ? 1 : PY) : 1][(TABLE && has_x) ? VEC : 1][(TABLE && has_x) ? NQ : 1];
-        if constexpr (TABLE && has_x) {
+        // TABLE, 2-D strips: the x-axis weights of this thread's own points stay in registers for the whole item
+        // (3-D tiles stage them in shared memory, see below: registers are what the 2.5-D queue needs)
+        constexpr bool WXREG = TABLE && has_x && !MID;
+        T wx[WXREG ? PY : 1][WXREG ? VEC : 1][WXREG ? NQ : 1];
+        if constexpr (WXREG) {
 #pragma unroll
-            for (int j = 0; j < (MID ? 1 : PY); ++j)
+            for (int j = 0; j < PY; ++j)
 #pragma unroll
                 for (int v = 0; v < VEC; ++v)
 #pragma unroll
                     for (int t = 0; t < NQ; ++t) wx[j][v][t] = __ldg(S.tab[0] + (long long)min(gx[j] + v, nx - 1) * NQ + t);
         }
-        const T* wyp[PY];                                      // TABLE: this thread's rows of the mid-axis weight table
-        if constexpr (TABLE && has_y) {
-#pragma unroll
-            for (int j = 0; j < PY; ++j) wyp[j] = S.tab[1] + (long long)min(gy[j], ny - 1) * NQ;
+        // TABLE: the mid-axis rows of this tile and the march-axis rows of this chunk are staged in shared memory by the
+        // compute warps (double-buffered per item: a warp can only be one item ahead of the slowest one, see the barrier)
+        const T* sWy = tabbuf + (q & 1) * G::TAB_ELEMS;
+        const T* sWz = sWy + G::TY * NQ;
+        const T* sWx = sWz + G::TAB_ZMAX * NQ;                // [NQ][TX]: tap-major, so that a lane's VEC weights of one tap are one 16-byte load
+        if constexpr (TABLE) {
+            T* wbuf = tabbuf + (q & 1) * G::TAB_ELEMS;
+            if constexpr (has_x && MID) {
+                for (int i = threadIdx.x; i < G::TX * NQ; i += NW * 32)
+                    wbuf[(G::TY + G::TAB_ZMAX) * NQ + (i % NQ) * G::TX + i / NQ] = __ldg(S.tab[0] + (long long)min(tx0 + i / NQ, nx - 1) * NQ + i % NQ);
+            }
+            if constexpr (has_y) {
+                for (int i = threadIdx.x; i < G::TY * NQ; i += NW * 32)
+                    wbuf[i] = __ldg(S.tab[1] + (long long)min(ty0 + i / NQ, ny - 1) * NQ + i % NQ);
+            }
+            if constexpr (has_z) {
+                for (int i = threadIdx.x; i < (zc1 - zc0) * NQ; i += NW * 32)
+                    wbuf[G::TY * NQ + i] = __ldg(S.tab[2] + (long long)(zc0 + S.row0_z + i / NQ) * NQ + i % NQ);
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");
         }
 
         // ---- priming: the first 2R planes only feed the queue (physical slots 1..2R; the first step writes slot 0) ----
@@ -408,10 +491,10 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                 __syncwarp();
                 if (lane == 0) mbar_arrive_u32(empty_u32 + 8u * slot_a);
             }
-            if (++slot_a == NS) { slot_a = 0; par_a ^= 1; }
+            if (++slot_a == ns) { slot_a = 0; par_a ^= 1; }
         }
         int slot_c = slot_a - R;                               // centre plane of the first step = R planes behind
-        if (slot_c < 0) slot_c += NS;
+        if (slot_c < 0) slot_c += ns;
         int z = zc0, ka = 2 * R;
 
         // One step = acquire plane z+R, compute and store centre plane z.  ROT = u >= 0: the new plane overwrites
@@ -451,7 +534,25 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
             const int gz = z + S.row0_z;
             T tot[PY][VEC];
             // ================= x operator: window = [R halo | VEC own (already in the queue) | R halo] =================
-            if constexpr (has_x) {
+            if constexpr (has_x && TABLE && MID) {
+                // per-point weights from shared memory, one 16-byte load per tap shared by the PY rows (same x)
+                T xw[PY][XW];
+#pragma unroll
+                for (int j = 0; j < PY; ++j) {
+                    load_x_halo<T, R>(pl + soff[j], xw[j]);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) { xw[j][R + v] = zq[j][v][P(R)]; tot[j][v] = T(0); }
+                }
+#pragma unroll
+                for (int t = 0; t < NQ; ++t) {
+                    T wv[VEC];
+                    ld_vec<T, VEC>(sWx + t * G::TX + lane * VEC, wv);
+#pragma unroll
+                    for (int j = 0; j < PY; ++j)
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) tot[j][v] = fma_t(wv[v], xw[j][v + t], tot[j][v]);
+                }
+            } else if constexpr (has_x) {
 #pragma unroll
                 for (int j = 0; j < PY; ++j) {
                     T xw[XW];
@@ -463,12 +564,14 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                         T a = T(0);
 #pragma unroll
                         for (int t = 0; t < NQ; ++t) {
-                            if constexpr (TABLE) a = fma_t(wx[MID ? 0 : j][v][t], xw[v + t], a);
+                            if constexpr (TABLE) a = fma_t(wx[j][v][t], xw[v + t], a);
                             else a = fma_t(S.w[0][t], xw[v + t], a);
                         }
                         tot[j][v] = a;
                     }
                 }
+            }
+            if constexpr (has_x) {
                 if (xface) {
 #pragma unroll
                     for (int j = 0; j < PY; ++j) {
@@ -502,7 +605,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                         const int t = r - j;
                         if (t >= 0 && t < NQ) {
                             T wyt;
-                            if constexpr (TABLE) wyt = __ldg(wyp[j] + t); else wyt = S.w[1][t];
+                            if constexpr (TABLE) wyt = sWy[(wy * PY + j) * NQ + t]; else wyt = S.w[1][t];
 #pragma unroll
                             for (int v = 0; v < VEC; ++v) acc[j][v] = fma_t(wyt, row[v], acc[j][v]);
                         }
@@ -526,7 +629,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                     T wz[NQ];
 #pragma unroll
                     for (int t = 0; t < NQ; ++t) {
-                        if constexpr (TABLE) wz[t] = __ldg(S.tab[2] + (long long)gz * NQ + t); else wz[t] = S.w[2][t];
+                        if constexpr (TABLE) wz[t] = sWz[(z - zc0) * NQ + t]; else wz[t] = S.w[2][t];
                     }
 #pragma unroll
                     for (int j = 0; j < PY; ++j) {
@@ -560,7 +663,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
             if (lane == 0) mbar_arrive_u32(empty_u32 + 8u * slot_c);
 #pragma unroll
             for (int j = 0; j < PY; ++j)
-                if (live[j]) st_vec<T, VEC>(ocur[j], tot[j]);
+                if (live[j]) { if (L.st_cs) st_vec_cs<T, VEC>(ocur[j], tot[j]); else st_vec<T, VEC>(ocur[j], tot[j]); }
 
             if constexpr (has_z && EDGE) {
                 // --- march-axis rows that touch a ghost, from the register queue -------------------------------
@@ -627,8 +730,8 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
             }
             // --- advance the ring and the output pointers ---------------------------------------------------
             ++z; ++ka;
-            if (++slot_a == NS) { slot_a = 0; par_a ^= 1; }
-            if (++slot_c == NS) slot_c = 0;
+            if (++slot_a == ns) { slot_a = 0; par_a ^= 1; }
+            if (++slot_c == ns) slot_c = 0;
 #pragma unroll
             for (int j = 0; j < PY; ++j) ocur[j] += S.osz;
         };
@@ -671,7 +774,7 @@ int32_t launch_variant2(const StarConfig& C, const void* u, void* du, long long 
     int dev = 0;
     DEO_CUDA(cudaGetDevice(&dev));
     if (attr_device != dev) {
-        DEO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
+        DEO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TABLE ? G::SMEM_TABLE : G::SMEM)));
         attr_device = dev;
     }
     const long long len = z1 - z0;
@@ -681,6 +784,7 @@ int32_t launch_variant2(const StarConfig& C, const void* u, void* du, long long 
     // plane-steps (one CTA per SM works through ceil(items / SMs) items, each costing its planes plus 2R priming
     // planes); never cut a face's one-sided rows.
     long long zmax = C.zchunk_max > 0 ? C.zchunk_max : len;
+    if (TABLE && zmax > G::TAB_ZMAX) zmax = G::TAB_ZMAX;
     if (zmax < 4 * R + 4) zmax = 4 * R + 4;
     long long zc = len;
     {
@@ -707,16 +811,52 @@ int32_t launch_variant2(const StarConfig& C, const void* u, void* du, long long 
     const bool fused = C.halo_flag != nullptr;
     if (fused && Lp.nchunks < 3) { set_error("star kernel: fused halo launch needs at least 3 chunks"); return DEO_ERR_UNSUPPORTED; }
     Lp.fused = fused ? 1 : 0;
+    {
+        // band = the largest whole number of tile rows that fits the grid (at least one row); one band when the layer fits
+        long long band = tiles;
+        const long long env_band = getenv("DEO_STAR2_BAND") ? atoll(getenv("DEO_STAR2_BAND")) : 0;
+        if (!fused && tiles > C.sm_count) band = (C.sm_count / tiles_x > 0 ? C.sm_count / tiles_x : 1) * tiles_x;
+        if (!fused && env_band > 0) band = ((env_band + tiles_x - 1) / tiles_x) * tiles_x;
+        if (band > tiles) band = tiles;
+        Lp.band = (int)band;
+    }
     Lp.halo_flag = fused ? C.halo_flag : nullptr;
     Lp.halo_expect = C.halo_expect; Lp.halo_sides = C.halo_sides;
     Lp.err_word = star2_rt().err_dev;
     Lp.sched = star2_rt().sched;
+    Lp.stagger_ns = getenv("DEO_STAR2_STAGGER_NS") ? atoi(getenv("DEO_STAR2_STAGGER_NS")) : 0;
+    Lp.pace_cycles = getenv("DEO_STAR2_PACE") ? atoi(getenv("DEO_STAR2_PACE")) : 0;
+    Lp.st_cs = getenv("DEO_STAR2_ST_CS") ? atoi(getenv("DEO_STAR2_ST_CS")) : 0;
+    Lp.ld_policy = getenv("DEO_STAR2_LD_POLICY") ? atoi(getenv("DEO_STAR2_LD_POLICY")) : 0;
+    // Prefetch depth: R + 6 ring slots (R + 1 live planes, 5 in flight).  Deeper rings only lengthen the queues in the
+    // memory system: the CTAs drift further apart and the halo rows / columns neighbouring tiles share fall out of L2
+    // before the second reader arrives (measured on 1024^3: 11 slots 330, 8 slots 354 Gpoints/s).
+    Lp.ns = G::NS < R + 6 ? G::NS : R + 6;
+    if (getenv("DEO_STAR2_NS")) { const int v = atoi(getenv("DEO_STAR2_NS")); if (v >= R + 4 && v <= G::NS) Lp.ns = v; }
+    Lp.trace = nullptr;
+    if (getenv("DEO_STAR2_TRACE")) {                      // debug: dumps the item schedule of this launch to the named file (synchronous)
+        static unsigned long long* buf = nullptr;
+        static size_t cap = 0;
+        if (cap < (size_t)Lp.n_items * 3) { if (buf) cudaFree(buf); cap = (size_t)Lp.n_items * 3; if (cudaMalloc(&buf, cap * 8) != cudaSuccess) { buf = nullptr; cap = 0; } }
+        Lp.trace = buf;
+    }
     DEO_REQUIRE(Lp.sched != nullptr, "star kernel: scheduler words could not be allocated");
     Lp.timeout_ns = C.halo_timeout_ns;
     Lp.accumulate = 0; Lp.axpy = 0; Lp.dt = 0.0;
     const unsigned grid = (unsigned)(Lp.n_items < C.sm_count ? Lp.n_items : C.sm_count);
-    kern<<<grid, G::THREADS, G::SMEM, s>>>(C.tmap, S, Lp, (const T*)u, (T*)du);
+    if (TABLE && zc > G::TAB_ZMAX) { set_error("star kernel: march-axis range too short to chunk"); return DEO_ERR_UNSUPPORTED; }
+    kern<<<grid, G::THREADS, TABLE ? G::SMEM_TABLE : G::SMEM, s>>>(C.tmap, S, Lp, (const T*)u, (T*)du);
     DEO_CUDA(cudaGetLastError());
+    if (Lp.trace) {
+        std::vector<unsigned long long> h((size_t)Lp.n_items * 3);
+        DEO_CUDA(cudaStreamSynchronize(s));
+        DEO_CUDA(cudaMemcpy(h.data(), Lp.trace, h.size() * 8, cudaMemcpyDeviceToHost));
+        if (FILE* f = fopen(getenv("DEO_STAR2_TRACE"), "w")) {
+            fprintf(f, "# tiles_x %d tiles_xy %d nchunks %d zchunk %d\n", Lp.tiles_x, Lp.tiles_xy, Lp.nchunks, Lp.zchunk);
+            for (int i = 0; i < Lp.n_items; ++i) fprintf(f, "%d %llu %llu %llu\n", i, h[3 * (size_t)i], h[3 * (size_t)i + 1], h[3 * (size_t)i + 2]);
+            fclose(f);
+        }
+    }
     return DEO_OK;
 }
 
