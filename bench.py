@@ -320,6 +320,12 @@ def main():
         print(f"[bench] WORLD_SIZE={world} != --gpus {args.gpus}; using WORLD_SIZE", file=sys.stderr)
     N = world
 
+    # stdout carries exactly ONE JSON line: anything a library prints there while we run (NCCL's version banner, ...) is
+    # sent to stderr instead; the real stdout comes back for the final print
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import ctypes as C
     import deo_b200 as D
     from deo_b200 import _lib
@@ -494,7 +500,10 @@ def main():
             line["cpu_baseline"] = cpu
         if configs is not None:
             line["configs"] = configs
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

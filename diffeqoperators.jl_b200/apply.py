@@ -150,6 +150,7 @@ class Plan:
         self.out_shape = tuple(out_shape)
         self.in_shape = tuple(s + 2 * int(p) for s, p in zip(out_shape, padded))
         self.dtype = np.dtype(dtype)
+        self.term_index = list(range(len(ops_axes)))      # plan op k  <->  term of the operator it was built from
 
     def __del__(self):
         try:
@@ -242,11 +243,13 @@ def build_plans(A, out_shape, in_shape, dtype, accumulate=False, flags=0, Q_over
         cpad = [False, padded[ax - 1], False]
         cin = tuple(s + 2 * int(p) for s, p in zip(cshape, cpad))
         plan = Plan([(L, 1) for L, _ in sub], [None, bc, None], cshape, cpad, T, accumulate or bool(plans), flags)
+        plan.term_index = [k for k, (L, _) in enumerate(terms) if L.axis == ax]
         plans.append((plan, cshape, cin))
     return plans
 
 
 _PLAN_CACHE_ATTR = "_deo_plan_cache"
+_PLAN_CACHE_MAX = 8          # entries per operator object (shape / dtype / boundary-operator variants); least recently used goes first
 
 
 def _coeff_versions(A):
@@ -254,12 +257,28 @@ def _coeff_versions(A):
 
 
 def _get_plans(A, out_shape, in_shape, dtype, accumulate, flags, Q_override=None):
+    """Cached plans of operator `A` for one (shapes, dtype, accumulate, boundary operator).  Coefficient changes
+    (`update_coefficients!`, `set_coefficients`, a time-dependent `coeff_func` in `A(du,u,p,t)`) do NOT create new plans:
+    the cached plan is refreshed in place with deo_plan_update_coefficients for the operators whose version moved, so a
+    time-stepping loop neither leaks device tables nor pays a plan build per step."""
     cache = A.__dict__.setdefault(_PLAN_CACHE_ATTR, {})
-    key = (tuple(out_shape), tuple(in_shape), np.dtype(dtype).str, bool(accumulate), flags, _coeff_versions(A), id(Q_override))
-    if key not in cache:
+    key = (tuple(out_shape), tuple(in_shape), np.dtype(dtype).str, bool(accumulate), flags, id(Q_override))
+    entry = cache.pop(key, None)
+    versions = _coeff_versions(A)
+    if entry is None:
         # the entry keeps Q_override alive, so its id() cannot be recycled for another boundary operator while cached
-        cache[key] = (build_plans(A, out_shape, in_shape, dtype, accumulate, flags, Q_override), Q_override)
-    return cache[key][0]
+        entry = [build_plans(A, out_shape, in_shape, dtype, accumulate, flags, Q_override), Q_override, versions]
+    elif entry[2] != versions:
+        terms = _terms(A)
+        for plan, _, _ in entry[0]:
+            for k, op_index in enumerate(plan.term_index):
+                if entry[2][op_index] != versions[op_index]:
+                    plan.update_coefficients(k, terms[op_index][0].coefficients)
+        entry[2] = versions
+    cache[key] = entry                      # (re)inserted last: dict order is the LRU order
+    while len(cache) > _PLAN_CACHE_MAX:
+        cache.pop(next(iter(cache)))
+    return entry[0]
 
 
 def _unwrap(u):

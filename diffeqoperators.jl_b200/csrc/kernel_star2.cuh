@@ -112,10 +112,7 @@ __device__ __forceinline__ bool rot_steps(F& f, Stop& stop) {
     else return false;
 }
 
-// One work item: tile origin and march-axis range.  Items are ordered chunk-major (every tile of chunk 0, then chunk
-// 1, ...): the CTAs of the grid work on neighbouring tiles of the same chunk at the same time, so the halo
-// rows / columns two tiles share are still in L2 when the second one asks.  Slab launches that wait for their halo
-// planes in the kernel schedule the first and the last chunk last.
+// One work item: tile origin and march-axis range.
 struct Star2Item { int tx0, ty0, zc0, zc1; };
 // Item order.  The x-y tiles are grouped into BANDS of about one grid's worth of tiles (whole tile rows); inside a band the
 // list runs chunk-major: every tile of the band for chunk 0, the same tiles for chunk 1, ...  Two kinds of reuse follow:
@@ -123,17 +120,26 @@ struct Star2Item { int tx0, ty0, zc0, zc1; };
 // L2), and a tile's next chunk is taken up right when its previous chunk ends, so its 2R priming planes -- the planes the
 // previous chunk read last -- are still in L2 too.  Plain chunk-major order over a layer larger than the grid loses the
 // second kind (the next chunk of a tile starts several item-times later).
+// Slab launches that wait for their halo planes in the kernel (fused): the same order over the chunks 1 .. nchunks-2, then
+// the first and the last chunk of every tile -- the only items that read planes arriving over NVLink -- at the very end.
 template <int TX, int TY, bool MID>
 __device__ __forceinline__ Star2Item star2_item(const Star2Launch& L, int it) {
-    const int per_band = L.band * L.nchunks;
-    const int b = it / per_band;
-    const int first = b * L.band;                                  // first tile of the band
-    const int bt = min(L.band, L.tiles_xy - first);                 // tiles in this band (the last one may be short)
-    const int r = it - b * per_band;
-    int chunk = r / bt;
-    const int tile = first + (r - chunk * bt);
-    // slab launches that wait for their halo planes in the kernel schedule the first and the last chunk last (one band)
-    if (L.fused) chunk = chunk < L.nchunks - 2 ? chunk + 1 : (chunk == L.nchunks - 2 ? 0 : L.nchunks - 1);
+    const int nch = L.fused ? L.nchunks - 2 : L.nchunks;           // chunks in the banded part of the list
+    int chunk, tile;
+    if (L.fused && it >= L.tiles_xy * nch) {
+        const int r = it - L.tiles_xy * nch;
+        chunk = r < L.tiles_xy ? 0 : L.nchunks - 1;
+        tile = r < L.tiles_xy ? r : r - L.tiles_xy;
+    } else {
+        const int per_band = L.band * nch;
+        const int b = it / per_band;
+        const int first = b * L.band;                              // first tile of the band
+        const int bt = min(L.band, L.tiles_xy - first);             // tiles in this band (the last one may be short)
+        const int r = it - b * per_band;
+        chunk = r / bt;
+        tile = first + (r - chunk * bt);
+        if (L.fused) chunk += 1;
+    }
     Star2Item I;
     I.tx0 = (tile % L.tiles_x) * TX;
     I.ty0 = MID ? (tile / L.tiles_x) * TY : 0;
@@ -815,8 +821,8 @@ int32_t launch_variant2(const StarConfig& C, const void* u, void* du, long long 
         // band = the largest whole number of tile rows that fits the grid (at least one row); one band when the layer fits
         long long band = tiles;
         const long long env_band = getenv("DEO_STAR2_BAND") ? atoll(getenv("DEO_STAR2_BAND")) : 0;
-        if (!fused && tiles > C.sm_count) band = (C.sm_count / tiles_x > 0 ? C.sm_count / tiles_x : 1) * tiles_x;
-        if (!fused && env_band > 0) band = ((env_band + tiles_x - 1) / tiles_x) * tiles_x;
+        if (tiles > C.sm_count) band = (C.sm_count / tiles_x > 0 ? C.sm_count / tiles_x : 1) * tiles_x;
+        if (env_band > 0) band = ((env_band + tiles_x - 1) / tiles_x) * tiles_x;
         if (band > tiles) band = tiles;
         Lp.band = (int)band;
     }
