@@ -12,6 +12,6 @@ from .operators import (CenteredDifference, UpwindDifference, DerivativeOperator
 from .bc import (RobinBC, GeneralBC, NeumannBC, DirichletBC, Dirichlet0BC, Neumann0BC, PeriodicBC,
                  MultiDimBC, MultiDimDirectionalBC, ComposedMultiDimBC, AffineBC, BoundaryPadded, compose)
 from .device import DeviceArray, zeros, sync
-from .apply import mul_, mul_alloc, Plan, build_plans
+from .apply import mul_, mul_alloc, step_, Plan, build_plans
 
 __all__ = [n for n in dir() if not n.startswith("_")]

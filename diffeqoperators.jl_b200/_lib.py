@@ -67,6 +67,7 @@ EXPORTS = {
     "deo_plan_destroy": [C.c_void_p],
     "deo_plan_update_coefficients": [C.c_void_p, C.c_int32, C.c_void_p],
     "deo_plan_apply": [C.c_void_p, C.c_void_p, C.c_void_p],
+    "deo_plan_apply_axpy": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double],
     "deo_plan_apply_n": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32],
     "deo_plan_apply_host": [C.c_void_p, C.c_void_p, C.c_void_p],
     "deo_plan_info": [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_int32)],

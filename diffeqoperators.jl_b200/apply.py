@@ -170,6 +170,10 @@ class Plan:
     def apply(self, du: DeviceArray, u: DeviceArray):
         _lib.check(_lib.load().deo_plan_apply(self._h, du._h, u._h))
 
+    def apply_axpy(self, out: DeviceArray, u: DeviceArray, dt: float):
+        """out = u + dt * (A u), fused into the kernel's store where the plan runs on a tiled kernel."""
+        _lib.check(_lib.load().deo_plan_apply_axpy(self._h, out._h, u._h, float(dt)))
+
     def apply_n(self, du: DeviceArray, u: DeviceArray, reps: int):
         _lib.check(_lib.load().deo_plan_apply_n(self._h, du._h, u._h, reps))
 
@@ -321,6 +325,20 @@ def mul_(du, A, u, *, overwrite=True, flags=0):
     for i, (plan, _, _) in enumerate(plans):
         plan.apply_host(du, uf)
     return du
+
+
+def step_(out, A, u, dt, *, flags=0):
+    """out = u + dt * (A*u): one explicit-Euler update with the AXPY fused into the operator application (the caller of
+    mul! in the reference's own examples, test/DerivativeOperators/3D_laplacian.jl:20-24).  Device arrays only."""
+    if not (isinstance(out, DeviceArray) and isinstance(u, DeviceArray)):
+        raise TypeError("step_ works on DeviceArray operands")
+    if out.shape != u.shape or out.dtype != u.dtype:
+        raise TypeError("out must have the shape and eltype of u")
+    plans = _get_plans(A, out.shape, u.shape, out.dtype, False, flags, None)
+    if len(plans) != 1:
+        raise NotImplementedError("step_ on > 3-D arrays with operators along several axes")
+    plans[0][0].apply_axpy(out, u, dt)
+    return out
 
 
 def mul_alloc(A, u, *, flags=0):

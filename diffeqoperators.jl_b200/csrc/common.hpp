@@ -207,6 +207,8 @@ int32_t launch_star(const deo_plan* plan, void* du, const void* u, long long z0,
 struct StarLimits { bool fusable = false; long long min_fused_planes = 0; };
 StarLimits star_limits(const deo_plan* plan);
 bool star_take_halo_timeout();
+bool star_can_axpy(const deo_plan* plan);
+void star_set_axpy(const deo_plan* plan, bool on, double dt);
 int32_t launch_star_fused(const deo_plan* plan, void* du, const void* u, long long cnt, cudaStream_t s, const int* halo_flag, int expect, int sides);
 // dist.cu
 void dist_forget_buffer(void* ptr);

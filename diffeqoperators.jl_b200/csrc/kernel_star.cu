@@ -307,7 +307,8 @@ static bool tile_fits(const deo_plan* plan, const StarConfig& cfg, bool mid) {
 int32_t star_configure(deo_plan* plan) {
     const int nd = plan->ndims;
     if (nd < 2 || nd > 3) return DEO_OK;
-    if (plan->accumulate) return DEO_OK;
+    const bool want_v2 = !(getenv("DEO_STAR_V") && atoi(getenv("DEO_STAR_V")) == 1);
+    if (plan->accumulate && !want_v2) return DEO_OK;                    // overwrite = false: persistent kernel only
     const size_t es = plan->elem();
     for (int a = 0; a < nd; ++a) if (plan->padded[a]) return DEO_OK;
     if (((size_t)plan->dims[0] * es) % 16 != 0) return DEO_OK;          // TMA: row pitch must be a multiple of 16 bytes
@@ -316,6 +317,7 @@ int32_t star_configure(deo_plan* plan) {
     const int paxis[3] = {0, mid ? 1 : -1, mid ? 2 : 1};                 // kernel axis -> plan axis
     auto cfg = std::make_shared<StarConfig>();
     cfg->mid = mid;
+    cfg->accumulate = plan->accumulate != 0;
     cfg->sm_count = rt().sm_count;
     const char* env_py = getenv("DEO_STAR_PY");
     cfg->py = env_py ? atoi(env_py) : 2;                    // 2 rows per thread, two CTAs per SM measured fastest on B200
@@ -453,6 +455,17 @@ StarLimits star_limits(const deo_plan* plan) {
     L.fusable = C.mid && C.zchunk_max > 0;
     L.min_fused_planes = 3LL * C.zchunk_max + 4 * C.R + 4;                 // at least 3 chunks whatever the chunk search picks (it only shortens chunks)
     return L;
+}
+
+// du = u + dt * (A u): the explicit-stepper update fused into the store of the persistent kernel.
+bool star_can_axpy(const deo_plan* plan) {
+    if (!plan->star) return false;
+    const StarConfig& C = *static_cast<const StarConfig*>(plan->star.get());
+    return C.v2 && !C.accumulate;
+}
+void star_set_axpy(const deo_plan* plan, bool on, double dt) {
+    StarConfig& C = *static_cast<StarConfig*>(plan->star.get());
+    C.axpy = on; C.dt = dt;
 }
 
 int32_t launch_star_fused(const deo_plan* plan, void* du, const void* u, long long cnt, cudaStream_t s, const int* halo_flag, int expect, int sides) {

@@ -67,6 +67,9 @@ struct StarConfig {
     int halo_expect = 0, halo_sides = 0;
     int group = -1;          // tiles per launch-order group (0: one wave; < 0: plain order) (DEO_STAR_GROUP)
     int sm_count = 0;
+    bool accumulate = false; // du += result (persistent kernel only)
+    bool axpy = false;       // du = u + dt * result, per launch (persistent kernel only)
+    double dt = 0.0;
     bool v2 = true;          // persistent warp-specialised kernel (kernel_star2.cuh); false: the first-generation kernel (DEO_STAR_V=1)
     unsigned long long halo_timeout_ns = 30ull * 1000000000ull;   // slab launches: bound of the in-kernel wait for the neighbours' halo planes
 };

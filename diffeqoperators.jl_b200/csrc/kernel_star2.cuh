@@ -539,6 +539,8 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
             const T* pl = planes + slot_c * PLANE_ELEMS;
             const int gz = z + S.row0_z;
             T tot[PY][VEC];
+            T pk[EDGE ? PY : 1][EDGE ? VEC : 1];               // EDGE: march-axis term of a high-face row, parked in du earlier
+            bool parked = false;
             // ================= x operator: window = [R halo | VEC own (already in the queue) | R halo] =================
             if constexpr (has_x && TABLE && MID) {
                 // per-point weights from shared memory, one 16-byte load per tap shared by the PY rows (same x)
@@ -648,14 +650,14 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                         }
                     }
                 } else if (z_high_edge) {                  // the term was parked in du when the queue held its planes
+                    if constexpr (EDGE) {
+                        parked = true;
 #pragma unroll
-                    for (int j = 0; j < PY; ++j) {
-                        T a[VEC];
+                        for (int j = 0; j < PY; ++j) {
 #pragma unroll
-                        for (int v = 0; v < VEC; ++v) a[v] = T(0);
-                        if (live[j]) ld_vec<T, VEC>(ocur[j], a);
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) tot[j][v] = (has_x || has_y) ? tot[j][v] + a[v] : a[v];
+                            for (int v = 0; v < VEC; ++v) { pk[j][v] = T(0); if (!(has_x || has_y)) tot[j][v] = T(0); }
+                            if (live[j]) ld_vec<T, VEC>(ocur[j], pk[j]);
+                        }
                     }
                 } else if (!(has_x || has_y)) {            // low edge row of a march-axis-only plan: its term arrives later
 #pragma unroll
@@ -667,6 +669,32 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
             // release the centre plane's slot, then store
             __syncwarp();
             if (lane == 0) mbar_arrive_u32(empty_u32 + 8u * slot_c);
+            // epilogue: du = result | du += result (overwrite = false, convolutions.jl:17-22) | du = u + dt * result (the
+            // explicit-stepper update fused into the store, cf. test/DerivativeOperators/3D_laplacian.jl:20-24)
+            if (L.accumulate | L.axpy) {                       // launch-uniform
+                const T sc = L.axpy ? (T)L.dt : T(1);
+#pragma unroll
+                for (int j = 0; j < PY; ++j) {
+                    if (!live[j]) continue;
+                    T base[VEC];
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) base[v] = T(0);
+                    if (L.accumulate && !parked) ld_vec<T, VEC>(ocur[j], base);   // a parked term already contains the old du
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        if (L.axpy) base[v] += zq[j][v][P(R)];
+                        tot[j][v] = fma_t(sc, tot[j][v], base[v]);
+                        if constexpr (EDGE) { if (parked) tot[j][v] += pk[j][v]; }
+                    }
+                }
+            } else if constexpr (EDGE) {
+                if (parked) {
+#pragma unroll
+                    for (int j = 0; j < PY; ++j)
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) tot[j][v] = (has_x || has_y) ? tot[j][v] + pk[j][v] : pk[j][v];
+                }
+            }
 #pragma unroll
             for (int j = 0; j < PY; ++j)
                 if (live[j]) { if (L.st_cs) st_vec_cs<T, VEC>(ocur[j], tot[j]); else st_vec<T, VEC>(ocur[j], tot[j]); }
@@ -698,7 +726,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                                 T s = fma_t(S.bw[2][0][r][0], gl[v], T(0));
 #pragma unroll
                                 for (int kk = 1; kk < TB; ++kk) s = fma_t(S.bw[2][0][r][kk], zq[j][v][kk - 1], s);
-                                old[v] = old[v] + s;
+                                old[v] = L.axpy ? fma_t((T)L.dt, s, old[v]) : old[v] + s;
                             }
                             st_vec<T, VEC>(dst, old);
                         }
@@ -728,6 +756,14 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
 #pragma unroll
                                 for (int kk = 0; kk < TB - 1; ++kk) s = fma_t(S.bw[2][1][r][kk], zq[j][v][kk], s);
                                 out[v] = fma_t(S.bw[2][1][r][TB - 1], gh[v], s);
+                            }
+                            if (L.accumulate | L.axpy) {           // parked term = [old du +] dt * term
+                                T prev[VEC];
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v) prev[v] = T(0);
+                                if (L.accumulate) ld_vec<T, VEC>(dst, prev);
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v) out[v] = fma_t(L.axpy ? (T)L.dt : T(1), out[v], prev[v]);
                             }
                             st_vec<T, VEC>(dst, out);
                         }
@@ -848,7 +884,7 @@ int32_t launch_variant2(const StarConfig& C, const void* u, void* du, long long 
     }
     DEO_REQUIRE(Lp.sched != nullptr, "star kernel: scheduler words could not be allocated");
     Lp.timeout_ns = C.halo_timeout_ns;
-    Lp.accumulate = 0; Lp.axpy = 0; Lp.dt = 0.0;
+    Lp.accumulate = C.accumulate ? 1 : 0; Lp.axpy = C.axpy ? 1 : 0; Lp.dt = C.dt;
     const unsigned grid = (unsigned)(Lp.n_items < C.sm_count ? Lp.n_items : C.sm_count);
     if (TABLE && zc > G::TAB_ZMAX) { set_error("star kernel: march-axis range too short to chunk"); return DEO_ERR_UNSUPPORTED; }
     kern<<<grid, G::THREADS, TABLE ? G::SMEM_TABLE : G::SMEM, s>>>(C.tmap, S, Lp, (const T*)u, (T*)du);

@@ -133,6 +133,10 @@ int32_t deo_plan_update_coefficients(deo_plan *plan, int32_t op, const void *coe
 /* mul!(du, A, u): convolutions.jl:17-22 (1-D), derivative_operator_functions.jl:18-69 (N-D),
  * ghost_derivative_operator.jl:15-24 (L*Q), composite_operators.jl:64-65,:76-83 (sums). */
 int32_t deo_plan_apply(deo_plan *plan, deo_buffer *du, const deo_buffer *u);
+/* out = u + dt * (A u): the update every explicit stepper performs right after mul! (test/DerivativeOperators/
+ * 3D_laplacian.jl:20-24, heat_equation.jl:30-33), fused into the store of the tiled kernels: one read of u and one
+ * write of out per point instead of mul! followed by an AXPY pass.  u must have the shape of the result. */
+int32_t deo_plan_apply_axpy(deo_plan *plan, deo_buffer *out, const deo_buffer *u, double dt);
 /* `reps` back-to-back applications replayed from one CUDA graph ("repeated mul!"). */
 int32_t deo_plan_apply_n(deo_plan *plan, deo_buffer *du, const deo_buffer *u, int32_t reps);
 /* Host-buffer form of mul!: H2D copy of u, apply, D2H copy of du, synchronous. */

@@ -396,6 +396,40 @@ def test_overwrite_false_accumulates(D, O):
     assert_close(du, want, np.float64, "overwrite=false")
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape,a", [((96, 70, 41), 4), ((200, 37, 30), 6), ((300, 75), 4)])
+def test_tiled_accumulate_and_fused_axpy(D, O, dtype, shape, a):
+    """overwrite = false (convolutions.jl:17-22) and the fused explicit-stepper update u + dt*(A u)
+    (3D_laplacian.jl:20-24) on the tiled kernels: every face, every march-axis edge row."""
+    nd = len(shape)
+    h = tuple(1.0 / (s + 1) for s in shape)
+    A, Bs = _laplacian_pair(shape, a, h, dtype)
+    Q = D.compose(*D.RobinBC((1.0, 0.5, 0.25), (1.0, -0.5, 0.75), h, 1, shape, dtype=dtype))
+    bcs = {ax + 1: O.RobinBC((1.0, 0.5, 0.25), (1.0, -0.5, 0.75), h[ax], 1, dtype) for ax in range(nd)}
+    u = uniform_field(shape, dtype, seed=5)
+    old = uniform_field(shape, dtype, seed=6)
+    want = O.apply_sum(Bs, u, bcs).astype(np.float64)
+    G = A * Q
+    ud = D.DeviceArray.from_host(u)
+    # accumulate
+    dud = D.DeviceArray.from_host(old)
+    D.mul_(dud, G, ud, overwrite=False)
+    plan = D.apply._get_plans(G, shape, shape, dtype, True, 0)[0][0]
+    assert plan.info[0].startswith("star"), plan.info
+    scale = np.abs(want).max()
+    assert np.abs(dud.to_host() - (old.astype(np.float64) + want)).max() <= TOL[np.dtype(dtype)] * scale
+    # fused AXPY
+    dt = 1e-6
+    out = D.DeviceArray(shape, dtype)
+    D.step_(out, G, ud, dt)
+    ref = u.astype(np.float64) + dt * want
+    assert np.abs(out.to_host() - ref).max() <= TOL[np.dtype(dtype)] * max(np.abs(ref).max(), dt * scale)
+    # ... and through a plan that does not fuse (per-point kernel + update kernel)
+    out2 = D.DeviceArray(shape, dtype)
+    D.step_(out2, G, ud, dt, flags=D._lib.DEO_FLAG_FORCE_GENERIC)
+    assert np.abs(out2.to_host() - ref).max() <= TOL[np.dtype(dtype)] * max(np.abs(ref).max(), dt * scale)
+
+
 def test_update_coefficients_and_scalar_scaling(D, O):
     n = 200
     u = uniform_field(n, np.float64, seed=91)
