@@ -79,13 +79,24 @@ def _op_desc(op: DerivativeOperator, axis0: int, keep: _Keep) -> _lib.OpDesc:
     return d
 
 
-def _bc_desc(bc, T, keep: _Keep) -> _lib.BcDesc:
+def _bc_desc(bc, T, keep: _Keep, ndims: int = 1) -> _lib.BcDesc:
     d = _lib.BcDesc()
     if bc is None:
         d.kind = _lib.DEO_BC_NONE
         return d
     if isinstance(bc, PeriodicBC):
-        d.kind = _lib.DEO_BC_PERIODIC
+        if ndims > 1:
+            # On arrays the reference's periodic ghosts are lower = u[1, ...], upper = u[end, ...] of the SAME pencil
+            # (multi_dim_bc_operators.jl:221-228) -- literally the affine BC a = [1], b = 0, which every
+            # kernel (tiled ones included) evaluates exactly: fma(1, u, 0) + 0 == u.
+            one, zero = np.ones(1, dtype=T), np.zeros(1, dtype=T)
+            d.kind = _lib.DEO_BC_AFFINE
+            d.per_face = 0
+            d.K_l = d.K_r = 1
+            d.a_l, d.a_r = keep.ptr(one, T), keep.ptr(one, T)
+            d.b_l, d.b_r = keep.ptr(zero, T), keep.ptr(zero, T)
+            return d
+        d.kind = _lib.DEO_BC_PERIODIC          # vectors: l = u[end], r = u[1] (bc_operators.jl:192): the wrap-around read
         return d
     if isinstance(bc, AffineBC):
         d.kind = _lib.DEO_BC_AFFINE
@@ -137,7 +148,7 @@ class Plan:
         desc.accumulate = int(accumulate)
         desc.flags = flags
         for a in range(nd):
-            desc.bc[a] = _bc_desc(bcs[a], dtype, keep)
+            desc.bc[a] = _bc_desc(bcs[a], dtype, keep, nd)
         h = C.c_void_p()
         L = _lib.load()
         if dist is not None:

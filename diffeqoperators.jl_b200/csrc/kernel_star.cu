@@ -49,6 +49,42 @@ int32_t dispatch_T(const StarConfig& C, const void* u, void* du, long long z0, l
     return DEO_ERR_UNSUPPORTED;
 }
 
+// Boundary data of kernel axis `ka` (plan axis `pa`): one affine BC for the whole face (constant bank), and -- persistent
+// kernel only -- per-pencil BC tables (multi_dim_bc_operators.jl:54-57) or a pre-padded input whose ghost layer is read
+// instead of computed (derivative_operator_functions.jl:27-69).
+template <typename T, int R>
+bool fill_bc(const deo_plan* plan, int pa, int ka, bool v2, StarParams<T, R>& S) {
+    constexpr int NQ = StarParams<T, R>::NQ;
+    const DevPlan<T>& P = *reinterpret_cast<const DevPlan<T>*>(plan->devplan.data());
+    S.padded[ka] = plan->padded[pa];
+    S.per_face[ka] = 0;
+    if (plan->padded[pa]) return v2;
+    const HostBC& H = plan->bc[pa];
+    if (H.d.kind != DEO_BC_AFFINE) return false;
+    const int Kmax = ka == 2 ? NQ : kStarMaxK;
+    if (H.d.K_l > Kmax || H.d.K_r > Kmax || H.d.K_l > kStarMaxK || H.d.K_r > kStarMaxK) return false;
+    S.K_l[ka] = H.d.K_l;
+    S.K_r[ka] = H.d.K_r;
+    if (H.d.per_face) {
+        if (!v2) return false;
+        S.per_face[ka] = 1;
+        S.pf_a_l[ka] = P.bc[pa].a_l; S.pf_b_l[ka] = P.bc[pa].b_l;
+        S.pf_a_r[ka] = P.bc[pa].a_r; S.pf_b_r[ka] = P.bc[pa].b_r;
+        return true;
+    }
+    const T* al = (const T*)H.a_l.data();
+    const T* ar = (const T*)H.a_r.data();
+    for (int t = 0; t < H.d.K_l; ++t) S.a_l[ka][t] = al[t];
+    for (int t = 0; t < H.d.K_r; ++t) S.a_r[ka][t] = ar[t];
+    S.b_l[ka] = *(const T*)H.b_l.data();
+    S.b_r[ka] = *(const T*)H.b_r.data();
+    if (ka == 2) {
+        for (int t = 0; t < H.d.K_l; ++t) S.azl_pad[t] = al[t];
+        for (int t = 0; t < H.d.K_r; ++t) S.azr_pad[NQ - H.d.K_r + t] = ar[t];
+    }
+    return true;
+}
+
 template <typename T, int R>
 bool fill_params(const deo_plan* plan, const int kaxis_of_plan_axis[3], bool mid, StarConfig& C) {
     using SP = StarParams<T, R>;
@@ -62,13 +98,15 @@ bool fill_params(const deo_plan* plan, const int kaxis_of_plan_axis[3], bool mid
     S.ny = mid ? P.n_out[1] : 1;
     S.nz = P.n_out[march_plan_axis];
     S.in_off_z = P.in_off[march_plan_axis];
+    S.in_off_x = P.in_off[0];
+    S.in_off_y = mid ? P.in_off[1] : 0;
     S.row0_z = P.row0[march_plan_axis];
     S.nglob_z = P.n_glob[march_plan_axis];
     S.isy = mid ? P.in_stride[1] : 0;
     S.osy = mid ? P.out_stride[1] : 0;
     S.isz = P.in_stride[march_plan_axis];
     S.osz = P.out_stride[march_plan_axis];
-    for (int a = 0; a < 3; ++a) { S.has[a] = 0; S.opidx[a] = -1; S.nedge[a] = 0; S.K_l[a] = S.K_r[a] = 0; }
+    for (int a = 0; a < 3; ++a) { S.has[a] = 0; S.opidx[a] = -1; S.nedge[a] = 0; S.K_l[a] = S.K_r[a] = 0; S.padded[a] = 0; S.per_face[a] = 0; }
     // the explicit rows live in device memory: fetch them back through the host copies kept in the plan
     for (int k = 0; k < P.nops; ++k) {
         const DevOp<T>& op = P.ops[k];
@@ -108,22 +146,7 @@ bool fill_params(const deo_plan* plan, const int kaxis_of_plan_axis[3], bool mid
             }
         }
         // boundary condition of this axis
-        const HostBC& H = plan->bc[op.axis];
-        if (H.d.kind != DEO_BC_AFFINE || H.d.per_face) return false;
-        const int Kmax = ka == 2 ? NQ : kStarMaxK;
-        if (H.d.K_l > Kmax || H.d.K_r > Kmax || H.d.K_l > kStarMaxK || H.d.K_r > kStarMaxK) return false;
-        S.K_l[ka] = H.d.K_l;
-        S.K_r[ka] = H.d.K_r;
-        const T* al = (const T*)H.a_l.data();
-        const T* ar = (const T*)H.a_r.data();
-        for (int t = 0; t < H.d.K_l; ++t) S.a_l[ka][t] = al[t];
-        for (int t = 0; t < H.d.K_r; ++t) S.a_r[ka][t] = ar[t];
-        S.b_l[ka] = *(const T*)H.b_l.data();
-        S.b_r[ka] = *(const T*)H.b_r.data();
-        if (ka == 2) {
-            for (int t = 0; t < H.d.K_l; ++t) S.azl_pad[t] = al[t];
-            for (int t = 0; t < H.d.K_r; ++t) S.azr_pad[NQ - H.d.K_r + t] = ar[t];
-        }
+        if (!fill_bc<T, R>(plan, op.axis, ka, C.v2, S)) return false;
     }
     return true;
 }
@@ -175,6 +198,8 @@ bool fill_params_table(deo_plan* plan, const AxisRows (&axes)[3], const int plan
     S.ny = mid ? P.n_out[1] : 1;
     S.nz = P.n_out[march_plan_axis];
     S.in_off_z = P.in_off[march_plan_axis];
+    S.in_off_x = P.in_off[0];
+    S.in_off_y = mid ? P.in_off[1] : 0;
     S.row0_z = P.row0[march_plan_axis];
     S.nglob_z = P.n_glob[march_plan_axis];
     S.isy = mid ? P.in_stride[1] : 0;
@@ -182,7 +207,7 @@ bool fill_params_table(deo_plan* plan, const AxisRows (&axes)[3], const int plan
     S.isz = P.in_stride[march_plan_axis];
     S.osz = P.out_stride[march_plan_axis];
     for (int ka = 0; ka < 3; ++ka) {
-        S.has[ka] = 0; S.opidx[ka] = -1; S.nedge[ka] = 0; S.K_l[ka] = S.K_r[ka] = 0; S.tab[ka] = nullptr;
+        S.has[ka] = 0; S.opidx[ka] = -1; S.nedge[ka] = 0; S.K_l[ka] = S.K_r[ka] = 0; S.tab[ka] = nullptr; S.padded[ka] = 0; S.per_face[ka] = 0;
         const AxisRows& A = axes[ka];
         if (A.ops.empty()) continue;
         S.has[ka] = 1;
@@ -215,22 +240,7 @@ bool fill_params_table(deo_plan* plan, const AxisRows (&axes)[3], const int plan
         S.tab[ka] = (const T*)blob->p;
         plan->blobs.push_back(std::move(blob));
         // boundary condition of this axis
-        const HostBC& H = plan->bc[plan_axis_of_kaxis[ka]];
-        if (H.d.kind != DEO_BC_AFFINE || H.d.per_face) return false;
-        const int Kmax = ka == 2 ? NQ : kStarMaxK;
-        if (H.d.K_l > Kmax || H.d.K_r > Kmax || H.d.K_l > kStarMaxK || H.d.K_r > kStarMaxK) return false;
-        S.K_l[ka] = H.d.K_l;
-        S.K_r[ka] = H.d.K_r;
-        const T* al = (const T*)H.a_l.data();
-        const T* ar = (const T*)H.a_r.data();
-        for (int t = 0; t < H.d.K_l; ++t) S.a_l[ka][t] = al[t];
-        for (int t = 0; t < H.d.K_r; ++t) S.a_r[ka][t] = ar[t];
-        S.b_l[ka] = *(const T*)H.b_l.data();
-        S.b_r[ka] = *(const T*)H.b_r.data();
-        if (ka == 2) {
-            for (int t = 0; t < H.d.K_l; ++t) S.azl_pad[t] = al[t];
-            for (int t = 0; t < H.d.K_r; ++t) S.azr_pad[NQ - H.d.K_r + t] = ar[t];
-        }
+        if (!fill_bc<T, R>(plan, plan_axis_of_kaxis[ka], ka, C.v2, S)) return false;
     }
     return true;
 }
@@ -310,8 +320,13 @@ int32_t star_configure(deo_plan* plan) {
     const bool want_v2 = !(getenv("DEO_STAR_V") && atoi(getenv("DEO_STAR_V")) == 1);
     if (plan->accumulate && !want_v2) return DEO_OK;                    // overwrite = false: persistent kernel only
     const size_t es = plan->elem();
-    for (int a = 0; a < nd; ++a) if (plan->padded[a]) return DEO_OK;
-    if (((size_t)plan->dims[0] * es) % 16 != 0) return DEO_OK;          // TMA: row pitch must be a multiple of 16 bytes
+    // Pre-padded input (the ghost layer is part of the array): persistent kernel only, and not along the contiguous axis --
+    // there the input row is shifted by ONE element against the output row, so the 16-byte alignment TMA wants for a box's
+    // first element (a box starting at an odd Float64 index is an illegal instruction) and the 16-byte vector stores of du
+    // cannot both hold.  Such plans stay on the per-point kernel.
+    if (plan->padded[0]) return DEO_OK;
+    for (int a = 0; a < nd; ++a) if (plan->padded[a] && (!want_v2 || plan->slab_axis >= 0)) return DEO_OK;
+    if (((size_t)plan->in_dim(0) * es) % 16 != 0) return DEO_OK;       // TMA: row pitch must be a multiple of 16 bytes
     const bool mid = nd == 3;
     const int kaxis[3] = {0, mid ? 1 : 2, mid ? 2 : -1};                 // plan axis -> kernel axis (x, mid, march)
     const int paxis[3] = {0, mid ? 1 : -1, mid ? 2 : 1};                 // kernel axis -> plan axis

@@ -36,9 +36,14 @@ struct StarParams {
     int nx, ny, nz;              // local output extents along the kernel axes (x, mid, march); ny == 1 without a mid axis
     int has[3];                  // an operator acts along kernel axis a
     int opidx[3];                // its index in the plan
-    int in_off_z, row0_z, nglob_z, pad0_;
+    int in_off_z, row0_z, nglob_z, in_off_x;
     long long isy, isz, osy, osz;
-    int nedge[3], pad1_[3];      // rows per face whose stencil touches the ghost (= operator radius)
+    int nedge[3];                // rows per face whose stencil touches the ghost (= operator radius)
+    int in_off_y;                // input index = output index + in_off (1 where the input carries a ghost layer; slab halo along the march axis)
+    int padded[3];               // persistent kernel: the ghosts of this axis come from the input array (pre-padded input), not from a BC
+    int per_face[3];             // persistent kernel: one affine BC per boundary pencil (MultiDimDirectionalBC.BCs), tables below
+    int pad2_;
+    const T *pf_a_l[3], *pf_b_l[3], *pf_a_r[3], *pf_b_r[3];   // device tables [face][K] / [face], faces column-major over the other axes
     int K_l[3], K_r[3];
     T a_l[3][kStarMaxK], a_r[3][kStarMaxK];
     T b_l[3], b_r[3];

@@ -156,7 +156,7 @@ __device__ __forceinline__ Star2Item star2_item(const Star2Launch& L, int it) {
 //    the value of x = nx-ex+i (high) HX columns to the right of its owner.  Those cells hold nothing but the TMA's
 //    out-of-bounds zeros on a face tile.
 template <typename T, int R, bool MID, int SIDE>
-__device__ __forceinline__ void star2_fix_x(const StarParams<T, R>& S, T* pl, int tx0, int ty0, int nx, int ny, int ex, int lane) {
+__device__ __forceinline__ void star2_fix_x(const StarParams<T, R>& S, T* pl, int tx0, int ty0, int nx, int ny, int ex, int lane, int gzp) {
     using G = Star2Geom<T, R, MID>;
     constexpr int TB = 2 * R + 2, HX = G::HX, PITCH = G::PITCH;
 #pragma unroll 1
@@ -165,12 +165,22 @@ __device__ __forceinline__ void star2_fix_x(const StarParams<T, R>& S, T* pl, in
         T* rowl = pl + (MID ? (R + rr) * PITCH : 0);      // local row
         const T* row = rowl + HX - tx0;                  // row[x] = value at global x
         const int K = SIDE ? S.K_r[0] : S.K_l[0];
-        const T* a = SIDE ? S.a_r[0] : S.a_l[0];
         const T* arow = row + (SIDE ? nx - K : 0);
         T gh = T(0);
+        if (S.padded[0]) {                               // pre-padded input: the ghost is the array's own outer layer
+            gh = SIDE ? row[nx] : row[-1];
+        } else if (S.per_face[0]) {                      // one BC per boundary pencil: faces column-major over (mid, march)
+            const long long face = (long long)(ty0 + rr) + (long long)ny * gzp;
+            const T* a = (SIDE ? S.pf_a_r[0] : S.pf_a_l[0]) + face * K;
 #pragma unroll 1
-        for (int kk = 0; kk < K; ++kk) gh = fma_t(a[kk], arow[kk], gh);
-        gh += SIDE ? S.b_r[0] : S.b_l[0];
+            for (int kk = 0; kk < K; ++kk) gh = fma_t(__ldg(a + kk), arow[kk], gh);
+            gh += __ldg((SIDE ? S.pf_b_r[0] : S.pf_b_l[0]) + face);
+        } else {
+            const T* a = SIDE ? S.a_r[0] : S.a_l[0];
+#pragma unroll 1
+            for (int kk = 0; kk < K; ++kk) gh = fma_t(a[kk], arow[kk], gh);
+            gh += SIDE ? S.b_r[0] : S.b_l[0];
+        }
         const T* qrow = SIDE ? row + (nx + 1 - TB) : row - 1;   // qrow[k] = q[k] (low) / q[n+2-TB+k] (high)
         T q[TB];
 #pragma unroll
@@ -190,24 +200,37 @@ __device__ __forceinline__ void star2_fix_x(const StarParams<T, R>& S, T* pl, in
 // y: lane <-> one 16-byte vector of columns (conflict-free vector loads).  Row y = i (low) is parked R rows above its owner,
 //    i.e. in local row i; row ny-ey+i (high) R rows below its owner.
 template <typename T, int R, int SIDE>
-__device__ __forceinline__ void star2_fix_y(const StarParams<T, R>& S, T* pl, int ty0, int ny, int ey, int lane) {
+__device__ __forceinline__ void star2_fix_y(const StarParams<T, R>& S, T* pl, int tx0, int ty0, int nx, int ny, int ey, int lane, int gzp) {
     using G = Star2Geom<T, R, true>;
     constexpr int TB = 2 * R + 2, HX = G::HX, PITCH = G::PITCH, VEC = G::VEC;
     T* colbase = pl + (R - ty0) * PITCH + HX + lane * VEC;      // colbase[y*PITCH + v] = value at global row y
     const int K = SIDE ? S.K_r[1] : S.K_l[1];
-    const T* a = SIDE ? S.a_r[1] : S.a_l[1];
     T gh[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) gh[v] = T(0);
+    if (S.padded[1]) {                                   // pre-padded input: the ghost row is part of the plane
+        ld_vec<T, VEC>(colbase + (SIDE ? ny : -1) * PITCH, gh);
+    } else if (S.per_face[1]) {                          // one BC per boundary pencil: faces column-major over (x, march)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            const long long face = (long long)min(tx0 + lane * VEC + v, nx - 1) + (long long)nx * gzp;
+            const T* a = (SIDE ? S.pf_a_r[1] : S.pf_a_l[1]) + face * K;
 #pragma unroll 1
-    for (int kk = 0; kk < K; ++kk) {
-        T val[VEC];
-        ld_vec<T, VEC>(colbase + ((SIDE ? ny - K : 0) + kk) * PITCH, val);
+            for (int kk = 0; kk < K; ++kk) gh[v] = fma_t(__ldg(a + kk), colbase[((SIDE ? ny - K : 0) + kk) * PITCH + v], gh[v]);
+            gh[v] += __ldg((SIDE ? S.pf_b_r[1] : S.pf_b_l[1]) + face);
+        }
+    } else {
+        const T* a = SIDE ? S.a_r[1] : S.a_l[1];
+#pragma unroll 1
+        for (int kk = 0; kk < K; ++kk) {
+            T val[VEC];
+            ld_vec<T, VEC>(colbase + ((SIDE ? ny - K : 0) + kk) * PITCH, val);
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) gh[v] = fma_t(a[kk], val[v], gh[v]);
+            for (int v = 0; v < VEC; ++v) gh[v] = fma_t(a[kk], val[v], gh[v]);
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) gh[v] += SIDE ? S.b_r[1] : S.b_l[1];
     }
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) gh[v] += SIDE ? S.b_r[1] : S.b_l[1];
     const T* qcol = colbase + (SIDE ? ny + 1 - TB : -1) * PITCH;   // qcol[k*PITCH] = q[k] / q[n+2-TB+k]
 #pragma unroll
     for (int i = 0; i < R; ++i) {
@@ -333,12 +356,12 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                     const int pz = I.zc0 - R + k + S.in_off_z;
                     T* dst = planes + (size_t)slot * PLANE_ELEMS;
                     if constexpr (MID) {
-                        if (L.ld_policy) tma_load_3d_hint(dst, &tmap, &full[slot], I.tx0 - HX, I.ty0 - R, pz, policy);
-                        else tma_load_3d(dst, &tmap, &full[slot], I.tx0 - HX, I.ty0 - R, pz);
+                        if (L.ld_policy) tma_load_3d_hint(dst, &tmap, &full[slot], I.tx0 - HX + S.in_off_x, I.ty0 - R + S.in_off_y, pz, policy);
+                        else tma_load_3d(dst, &tmap, &full[slot], I.tx0 - HX + S.in_off_x, I.ty0 - R + S.in_off_y, pz);
                     } else {
 #pragma unroll
                         for (int b = 0; b < G::NBOX; ++b)
-                            tma_load_3d(dst + b * G::BOXW, &tmap, &full[slot], I.tx0 - HX + b * G::BOXW, 0, pz);
+                            tma_load_3d(dst + b * G::BOXW, &tmap, &full[slot], I.tx0 - HX + S.in_off_x + b * G::BOXW, 0, pz);
                     }
                 }
                 if (L.trace) L.trace[3 * item + 1] = global_ns();
@@ -375,13 +398,14 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                 mbar_wait_u32(full_u32 + 8u * slot, (g / ns) & 1);
                 if (face && k >= R && k < n - R) {             // only planes that become a centre plane are read by the x / y parts
                     T* pl = planes + (size_t)slot * PLANE_ELEMS;
+                    const int gzp = I.zc0 - R + k + S.row0_z;        // global march-axis index of this plane
                     if constexpr (has_x) {
-                        if (f_xlo) star2_fix_x<T, R, MID, 0>(S, pl, I.tx0, I.ty0, nx, ny, ex, lane);
-                        if (f_xhi) star2_fix_x<T, R, MID, 1>(S, pl, I.tx0, I.ty0, nx, ny, ex, lane);
+                        if (f_xlo) star2_fix_x<T, R, MID, 0>(S, pl, I.tx0, I.ty0, nx, ny, ex, lane, gzp);
+                        if (f_xhi) star2_fix_x<T, R, MID, 1>(S, pl, I.tx0, I.ty0, nx, ny, ex, lane, gzp);
                     }
                     if constexpr (has_y) {
-                        if (f_ylo) star2_fix_y<T, R, 0>(S, pl, I.ty0, ny, ey, lane);
-                        if (f_yhi) star2_fix_y<T, R, 1>(S, pl, I.ty0, ny, ey, lane);
+                        if (f_ylo) star2_fix_y<T, R, 0>(S, pl, I.tx0, I.ty0, nx, ny, ey, lane, gzp);
+                        if (f_yhi) star2_fix_y<T, R, 1>(S, pl, I.tx0, I.ty0, nx, ny, ey, lane, gzp);
                     }
                     // the parked values are generic-proxy writes into a slot the TMA (async proxy) overwrites later
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -712,9 +736,20 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
 #pragma unroll
                         for (int v = 0; v < VEC; ++v) {
                             T s = T(0);
+                            if (S.padded[2]) {              // pre-padded input: the ghost plane is the array's first plane
+                                s = __ldg(u + (long long)(gx[j] + v + S.in_off_x) + (long long)(gy[j] + S.in_off_y) * S.isy);
+                            } else if (S.per_face[2]) {     // one BC per boundary pencil: faces column-major over (x, mid)
+                                const long long face = (long long)(gx[j] + v) + (long long)nx * gy[j];
+                                const T* a = S.pf_a_l[2] + face * S.K_l[2];
 #pragma unroll
-                            for (int m = 0; m < NQ; ++m) s = fma_t(S.azl_pad[m], zq[j][v][m], s);
-                            gl[v] = s + S.b_l[2];
+                                for (int m = 0; m < NQ; ++m) if (m < S.K_l[2]) s = fma_t(__ldg(a + m), zq[j][v][m], s);
+                                s += __ldg(S.pf_b_l[2] + face);
+                            } else {
+#pragma unroll
+                                for (int m = 0; m < NQ; ++m) s = fma_t(S.azl_pad[m], zq[j][v][m], s);
+                                s += S.b_l[2];
+                            }
+                            gl[v] = s;
                         }
 #pragma unroll 1
                         for (int r = 0; r < ez; ++r) {
@@ -742,9 +777,22 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
 #pragma unroll
                         for (int v = 0; v < VEC; ++v) {
                             T s = T(0);
+                            if (S.padded[2]) {              // pre-padded input: the ghost plane is the array's last plane
+                                s = __ldg(u + (long long)(gx[j] + v + S.in_off_x) + (long long)(gy[j] + S.in_off_y) * S.isy +
+                                          (long long)(S.nglob_z + 1) * S.isz);
+                            } else if (S.per_face[2]) {
+                                const long long face = (long long)(gx[j] + v) + (long long)nx * gy[j];
+                                const int K = S.K_r[2];
+                                const T* a = S.pf_a_r[2] + face * K;
 #pragma unroll
-                            for (int m = 0; m < NQ; ++m) s = fma_t(S.azr_pad[m], zq[j][v][m], s);
-                            gh[v] = s + S.b_r[2];
+                                for (int m = 0; m < NQ; ++m) if (m >= NQ - K) s = fma_t(__ldg(a + (m - (NQ - K))), zq[j][v][m], s);
+                                s += __ldg(S.pf_b_r[2] + face);
+                            } else {
+#pragma unroll
+                                for (int m = 0; m < NQ; ++m) s = fma_t(S.azr_pad[m], zq[j][v][m], s);
+                                s += S.b_r[2];
+                            }
+                            gh[v] = s;
                         }
 #pragma unroll 1
                         for (int r = 0; r < ez; ++r) {

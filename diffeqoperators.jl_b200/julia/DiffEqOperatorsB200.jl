@@ -118,9 +118,19 @@ function bc_desc(::Type{T}, bc::AffineBC, keep) where {T}
     push!(keep, al, ar, bl, br)
     BcDesc(1, 0, length(al), length(ar), pointer(al), pointer(bl), pointer(ar), pointer(br))
 end
+# vectors: l = u[end], r = u[1] (bc_operators.jl:192) -> DEO_BC_PERIODIC, the wrap-around read
 bc_desc(::Type{T}, ::PeriodicBC, keep) where {T} = BcDesc(2, 0, 0, 0, C_NULL, C_NULL, C_NULL, C_NULL)
+# arrays: the reference's periodic ghosts are lower = u[1, ...], upper = u[end, ...] of the same pencil
+# (multi_dim_bc_operators.jl:221-228), i.e. literally the affine BC a = [1], b = 0 -- which every tiled kernel takes
+function periodic_nd_desc(::Type{T}, keep) where {T}
+    one_, zero_ = T[1], T[0]
+    push!(keep, one_, zero_)
+    BcDesc(1, 0, 1, 1, pointer(one_), pointer(zero_), pointer(one_), pointer(zero_))
+end
 function bc_desc(::Type{T}, bcs::AbstractArray{<:AtomicBC}, keep) where {T}
-    all(b -> b === first(bcs), bcs) && return bc_desc(T, first(bcs), keep)     # fill(BC, perpsize(...)) : :97-100
+    if all(b -> b === first(bcs), bcs)                                         # fill(BC, perpsize(...)) : :97-100
+        return first(bcs) isa PeriodicBC ? periodic_nd_desc(T, keep) : bc_desc(T, first(bcs), keep)
+    end
     all(b -> b isa AffineBC, bcs) || error("per-pencil BC arrays must hold affine BCs")
     Kl = maximum(b -> length(b.a_l), bcs); Kr = maximum(b -> length(b.a_r), bcs)
     nf = length(bcs)
@@ -150,6 +160,7 @@ axis_of(::DerivativeOperator{T, N}) where {T, N} = N
 # ---- plans: built lazily from the operator object and cached per (operator, sizes) --------------------------
 mutable struct Plan
     handle::Ptr{Cvoid}
+    coeffs::Vector{Any}          # copies of the coefficient vectors the device tables were built from
 end
 const PLAN_CACHE = IdDict{Any, Dict{Any, Plan}}()
 
@@ -171,15 +182,25 @@ function build_plan(A, ::Type{T}, out_dims::Dims{N}, in_dims::Dims{N}, accumulat
                         length(ops), accumulate ? 1 : 0, pointer(ops), (bcs[1], bcs[2], bcs[3]), 0, 0))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve keep ops bcs check(ccall((:deo_plan_create, libdeo), Int32, (Ptr{PlanDesc}, Ptr{Ptr{Cvoid}}), desc, h))
-    p = Plan(h[])
+    p = Plan(h[], Any[copy(L.coefficients) for (L, _) in ts])
     finalizer(x -> ccall((:deo_plan_destroy, libdeo), Int32, (Ptr{Cvoid},), x.handle), p)
     p
 end
 
+# One plan per (operator, sizes).  update_coefficients! mutates A.coefficients in place on the host: the cached plan is
+# refreshed with deo_plan_update_coefficients for the operators whose vector changed -- never rebuilt, so a time-stepping
+# loop with a time-dependent coeff_func neither leaks device tables nor pays a plan build per step.
 function plan_for(A, ::Type{T}, out_dims, in_dims, accumulate) where {T}
-    # the coefficient vectors are part of the key: update_coefficients! mutates them in place
-    key = (T, out_dims, in_dims, accumulate, hash([L.coefficients for (L, _) in terms(A)]))
-    get!(() -> build_plan(A, T, out_dims, in_dims, accumulate), get!(() -> Dict{Any, Plan}(), PLAN_CACHE, A), key)
+    key = (T, out_dims, in_dims, accumulate)
+    p = get!(() -> build_plan(A, T, out_dims, in_dims, accumulate), get!(() -> Dict{Any, Plan}(), PLAN_CACHE, A), key)
+    for (k, (L, _)) in enumerate(terms(A))
+        if L.coefficients != p.coeffs[k]
+            c = collect(T, L.coefficients)
+            GC.@preserve c check(ccall((:deo_plan_update_coefficients, libdeo), Int32, (Ptr{Cvoid}, Int32, Ptr{Cvoid}), p.handle, k - 1, c))
+            p.coeffs[k] = copy(L.coefficients)
+        end
+    end
+    p
 end
 
 # ---- the methods the path sits behind -------------------------------------------------------------------------
@@ -212,7 +233,21 @@ function mul_host!(du::Array{T, N}, A::FusedOperator, u::Array{T, N}) where {T <
     du
 end
 
+# out = u + dt * (A*u): the update an explicit stepper performs right after mul! (test/DerivativeOperators/
+# 3D_laplacian.jl:20-24), fused into the store of the tiled kernels (deo_plan_apply_axpy).
+function step!(out::DeviceArray{T, N}, A::FusedOperator, u::DeviceArray{T, N}, dt::Real) where {T, N}
+    p = plan_for(A, T, size(out), size(u), false)
+    check(ccall((:deo_plan_apply_axpy, libdeo), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble), p.handle, out.handle, u.handle, Float64(dt)))
+    out
+end
+
+# Slab-decomposed plans (one process per GPU): host-buffer mul! on this rank's planes (deo_dist_plan_apply_host).
+function mul_host_slab!(du::Array{T, 3}, plan::Plan, u_own::Array{T, 3}) where {T <: Union{Float32, Float64}}
+    check(ccall((:deo_dist_plan_apply_host, libdeo), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), plan.handle, du, u_own))
+    du
+end
+
 # The (du,u,p,t) functor of src/DiffEqOperators.jl:66-75 works unchanged: update_coefficients! mutates
-# A.coefficients on the host, plan_for() sees the new hash and rebuilds (or call deo_plan_update_coefficients).
+# A.coefficients on the host, plan_for() notices and refreshes the cached plan in place.
 
 end # module

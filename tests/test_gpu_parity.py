@@ -367,6 +367,66 @@ def test_per_face_bc_tables(D, O):
         assert_close((A * Qd) * u, O.apply_axis(B, u, Qo), np.float64, f"per-face axis {ax}")
 
 
+def _kernel_of(D, G, out_shape, in_shape, dtype):
+    return D.apply._get_plans(G, out_shape, in_shape, dtype, False, 0)[0][0].info[0]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_tiled_kernel_takes_prepadded_perface_and_periodic_inputs(D, O, dtype):
+    """The shapes that used to fall back to the per-point kernel on the tiled kernel, several tiles wide
+    and tall: pre-padded dense input (derivative_operator_functions.jl:203,:466), per-pencil MultiDimBC arrays
+    (multi_dim_bc_operators.jl:54-57), N-D PeriodicBC (:221-228)."""
+    rng = np.random.default_rng(3)
+    for shape, a in [((200, 70, 37), 4), ((136, 44, 30), 6), ((264, 90), 4)]:
+        nd = len(shape)
+        h = tuple(1.0 / (s + 1) for s in shape)
+        # --- pre-padded input along every axis but the contiguous one: each operator reads its own axis' ghost layer of M
+        # (padding along dim 1 shifts rows by one element against du -- no 16-byte alignment for TMA -- and stays per-point)
+        pairs = [make_pair("centered", 2, a, h[ax - 1], shape[ax - 1], axis=ax, dtype=dtype) for ax in range(1, nd + 1)]
+        mshape = [shape[0]] + [s + 2 for s in shape[1:]]
+        M = uniform_field(mshape, dtype, seed=21)
+        A = pairs[1][0]
+        for pr in pairs[2:]:
+            A = A + pr[0]
+        du = np.zeros(shape, dtype=dtype, order="F")
+        D.mul_(du, A, M)
+        assert _kernel_of(D, A, shape, M.shape, dtype).startswith("star"), "pre-padded input must run tiled"
+        assert_close(du, O.apply_sum([pr[1] for pr in pairs[1:]], M, None), dtype, f"pre-padded {shape}")
+        A = pairs[0][0]
+        for pr in pairs[1:]:
+            A = A + pr[0]
+        # --- N-D periodic
+        u = uniform_field(shape, dtype, seed=22)
+        Qp = D.compose(*D.PeriodicBC(dtype, shape))
+        assert _kernel_of(D, A * Qp, shape, shape, dtype).startswith("star"), "N-D PeriodicBC must run tiled"
+        assert_close((A * Qp) * u, O.apply_sum([pr[1] for pr in pairs], u, {ax: O.PeriodicBC(dtype) for ax in range(1, nd + 1)}), dtype,
+                     f"periodic {shape}")
+    # --- per-pencil BC tables on every axis of a 3-D array (different Robin data and stencil length per pencil)
+    shape, a = (136, 44, 30), 4
+    h = tuple(1.0 / (s + 1) for s in shape)
+    u = uniform_field(shape, dtype, seed=23)
+    Qd, Qo = [], {}
+    for ax in (1, 2, 3):
+        face = tuple(s for i, s in enumerate(shape) if i != ax - 1)
+        arr = np.empty(face, dtype=object)
+        a_l = np.zeros(face + (3,), dtype=dtype); a_r = np.zeros(face + (3,), dtype=dtype)
+        b_l = np.zeros(face, dtype=dtype); b_r = np.zeros(face, dtype=dtype)
+        for idx in np.ndindex(*face):
+            order = int(rng.integers(1, 4))
+            q = D.RobinBC(tuple(rng.uniform(0.5, 2.0, 3)), tuple(rng.uniform(0.5, 2.0, 3)), h[ax - 1], order, dtype=dtype)
+            arr[idx] = q
+            a_l[idx][:order] = q.a_l; a_r[idx][3 - order:] = q.a_r; b_l[idx] = q.b_l; b_r[idx] = q.b_r
+        Qd.append(D.MultiDimBC[ax](arr))
+        nface = int(np.prod(face))
+        Qo[ax] = O.BC(a_l.reshape((nface, 3), order="F"), b_l.reshape(-1, order="F"), a_r.reshape((nface, 3), order="F"),
+                      b_r.reshape(-1, order="F"), dtype)
+    pairs = [make_pair("centered", 2, a, h[ax - 1], shape[ax - 1], axis=ax, dtype=dtype) for ax in (1, 2, 3)]
+    A = pairs[0][0] + pairs[1][0] + pairs[2][0]
+    G = A * D.compose(*Qd)
+    assert _kernel_of(D, G, shape, shape, dtype).startswith("star"), "per-pencil BC arrays must run tiled"
+    assert_close(G * u, O.apply_sum([pr[1] for pr in pairs], u, Qo), dtype, "per-pencil BC tables, 3 axes")
+
+
 def test_periodic_nd_quirk(D, O):
     """N-D PeriodicBC ghosts are lower=u[1,...], upper=u[end,...] (multi_dim_bc_operators.jl:221-228),
     the reverse of the 1-D rule (bc_operators.jl:192); reproduced as is."""
