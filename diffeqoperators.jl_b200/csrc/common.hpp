@@ -161,6 +161,13 @@ struct deo_plan {
 
     // device-side
     std::vector<std::unique_ptr<deo::DeviceBlob>> blobs;
+    // (Re)builds reuse the device allocations of the previous build in order (plan_upload) and send their contents with
+    // asynchronous copies out of a pinned staging arena, so deo_plan_update_coefficients neither allocates nor synchronises.
+    size_t blob_cursor = 0;
+    unsigned char* stage = nullptr;
+    size_t stage_cap = 0, stage_used = 0, stage_want = 0;
+    cudaEvent_t stage_ev = nullptr;
+    std::vector<std::vector<unsigned char>> host_brows;   // per operator: host copy of its explicit boundary rows (BRow<T>[])
     std::vector<unsigned char> devplan;     // DevPlan<T> bytes
     std::string kernel = "generic";
     int launches_per_apply = 1;
@@ -190,6 +197,9 @@ struct deo_plan {
 namespace deo {
 // plan_build.cu
 int32_t build_device_plan(deo_plan* plan);
+// Device copy of `bytes` host bytes owned by the plan: reuses the allocation the previous build made at the same position
+// when the size matches; the copy is stream-ordered on the library stream.  nullptr + *err on failure.
+void* plan_upload(deo_plan* plan, const void* host, size_t bytes, cudaError_t* err);
 struct HostRow { int start = 0, ntaps = 0; double w[kMaxBTaps]; };   // row r = sum_k w[k] * q[start + k]
 struct RowGenerator {                      // lazily enumerates the rows of one operator of a plan
     int n = 0;

@@ -175,12 +175,9 @@ bool fill_line(deo_plan* plan, std::vector<std::unique_ptr<RowGenerator>>& gens,
     if (!uniform) {
         std::vector<T> tabT(tab.size());
         for (size_t i = 0; i < tab.size(); ++i) tabT[i] = (T)tab[i];
-        auto blob = std::make_unique<DeviceBlob>();
-        if (cudaMalloc(&blob->p, tabT.size() * sizeof(T)) != cudaSuccess) return false;
-        blob->bytes = tabT.size() * sizeof(T);
-        if (cudaMemcpy(blob->p, tabT.data(), blob->bytes, cudaMemcpyHostToDevice) != cudaSuccess) return false;
-        S.tab = (const T*)blob->p;
-        plan->blobs.push_back(std::move(blob));
+        cudaError_t e;
+        S.tab = (const T*)plan_upload(plan, tabT.data(), tabT.size() * sizeof(T), &e);
+        if (!S.tab) { cudaGetLastError(); return false; }
     }
     if (!S.padded) {
         const HostBC& H = plan->bc[0];
@@ -198,7 +195,7 @@ bool fill_line(deo_plan* plan, std::vector<std::unique_ptr<RowGenerator>>& gens,
 template <typename T>
 bool fill_line_any(deo_plan* plan, std::vector<std::unique_ptr<RowGenerator>>& gens, LineConfig& C) {
     const int n = (int)plan->dims[0];
-    const size_t nblobs = plan->blobs.size();
+    const size_t cursor0 = plan->blob_cursor;
     for (int R = 1; R <= 4; ++R) {
         if (n < 4 * R + 4) return false;
         bool ok = false;
@@ -209,7 +206,7 @@ bool fill_line_any(deo_plan* plan, std::vector<std::unique_ptr<RowGenerator>>& g
             case 4: ok = fill_line<T, 4>(plan, gens, C); break;
         }
         if (ok) { C.R = R; return true; }
-        plan->blobs.resize(nblobs);
+        plan->blob_cursor = cursor0;
     }
     return false;
 }

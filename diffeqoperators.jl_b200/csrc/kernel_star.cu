@@ -123,7 +123,10 @@ bool fill_params(const deo_plan* plan, const int kaxis_of_plan_axis[3], bool mid
         if (n < 4 * R + 4) return false;
         S.nedge[ka] = r;                                   // rows 0..r-1 and n-r..n-1 read a ghost
         std::vector<BRow<T>> br((size_t)op.nlow + op.nhigh);
-        if (!br.empty() && cudaMemcpy(br.data(), op.brows, br.size() * sizeof(BRow<T>), cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+        if (!br.empty()) {                                    // the host copy kept by the plan: no device read-back
+            if ((size_t)k >= plan->host_brows.size() || plan->host_brows[(size_t)k].size() != br.size() * sizeof(BRow<T>)) return false;
+            memcpy(br.data(), plan->host_brows[(size_t)k].data(), br.size() * sizeof(BRow<T>));
+        }
         for (int i = 0; i < r; ++i) {                      // low face, global row i; tap k <-> q[k]
             if (i < op.nlow) {
                 const BRow<T>& b = br[i];
@@ -233,12 +236,9 @@ bool fill_params_table(deo_plan* plan, const AxisRows (&axes)[3], const int plan
             }
         std::vector<T> tabT(tab.size());
         for (size_t i = 0; i < tab.size(); ++i) tabT[i] = (T)tab[i];
-        auto blob = std::make_unique<DeviceBlob>();
-        if (cudaMalloc(&blob->p, tabT.size() * sizeof(T)) != cudaSuccess) return false;
-        blob->bytes = tabT.size() * sizeof(T);
-        if (cudaMemcpy(blob->p, tabT.data(), blob->bytes, cudaMemcpyHostToDevice) != cudaSuccess) return false;
-        S.tab[ka] = (const T*)blob->p;
-        plan->blobs.push_back(std::move(blob));
+        cudaError_t e;
+        S.tab[ka] = (const T*)plan_upload(plan, tabT.data(), tabT.size() * sizeof(T), &e);
+        if (!S.tab[ka]) { cudaGetLastError(); return false; }
         // boundary condition of this axis
         if (!fill_bc<T, R>(plan, plan_axis_of_kaxis[ka], ka, C.v2, S)) return false;
     }
@@ -402,10 +402,10 @@ int32_t star_configure(deo_plan* plan) {
     cfg->table = true;
     cfg->py = 2;
     cfg->nwy = 8;
-    const size_t nblobs = plan->blobs.size();
+    const size_t cursor0 = plan->blob_cursor;
     const bool ok = plan->dtype == DEO_F64 ? fill_params_table_R<double>(plan, axes, paxis, mid, *cfg)
                                            : fill_params_table_R<float>(plan, axes, paxis, mid, *cfg);
-    if (!ok || !tile_fits(plan, *cfg, mid)) { plan->blobs.resize(nblobs); return DEO_OK; }
+    if (!ok || !tile_fits(plan, *cfg, mid)) { plan->blob_cursor = cursor0; return DEO_OK; }
     cfg->nedge_march = (cfg->mask & 4) ? R : 0;
     plan->star = cfg;
     plan->kernel = "star-table";

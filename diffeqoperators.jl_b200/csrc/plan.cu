@@ -98,6 +98,16 @@ int32_t plan_from_desc(const deo_plan_desc* desc, deo_plan* plan) {
 }
 
 int32_t finalize_plan(deo_plan* plan) {
+    // staging arena: wait until the previous build's copies have left it (normally long done), grow it to what that
+    // build needed, then restart the allocation cursor so that this build reuses the same device blocks in the same order
+    if (plan->stage_ev) DEO_CUDA(cudaEventSynchronize(plan->stage_ev));
+    if (plan->stage_want > plan->stage_cap) {
+        if (plan->stage) cudaFreeHost(plan->stage);
+        plan->stage = nullptr; plan->stage_cap = 0;
+        if (cudaHostAlloc((void**)&plan->stage, plan->stage_want, cudaHostAllocDefault) == cudaSuccess) plan->stage_cap = plan->stage_want;
+        else { cudaGetLastError(); plan->stage = nullptr; }
+    }
+    plan->stage_used = 0; plan->stage_want = 0; plan->blob_cursor = 0;
     int32_t rc = build_device_plan(plan);
     if (rc) return rc;
     plan->kernel = "generic";
@@ -111,6 +121,9 @@ int32_t finalize_plan(deo_plan* plan) {
         if (rc) return rc;
     }
     if (plan->graph_exec) { cudaGraphExecDestroy(plan->graph_exec); plan->graph_exec = nullptr; }
+    if (plan->blobs.size() > plan->blob_cursor) plan->blobs.resize(plan->blob_cursor);   // blocks this build no longer uses
+    if (!plan->stage_ev) DEO_CUDA(cudaEventCreateWithFlags(&plan->stage_ev, cudaEventDisableTiming));
+    DEO_CUDA(cudaEventRecord(plan->stage_ev, rt().stream));
     return DEO_OK;
 }
 
@@ -183,6 +196,8 @@ int32_t deo_plan_destroy(deo_plan* plan) {
     if (plan->host_u) deo_buffer_free(plan->host_u);
     if (plan->host_du) deo_buffer_free(plan->host_du);
     for (cudaEvent_t e : plan->host_ev) cudaEventDestroy(e);
+    if (plan->stage_ev) cudaEventDestroy(plan->stage_ev);
+    if (plan->stage) cudaFreeHost(plan->stage);
     delete plan;
     return DEO_OK;
 }
@@ -192,7 +207,10 @@ int32_t deo_plan_update_coefficients(deo_plan* plan, int32_t op, const void* coe
     DEO_REQUIRE(op >= 0 && op < (int)plan->ops.size(), "deo_plan_update_coefficients: op %d out of range", op);
     HostOp& h = plan->ops[op];
     memcpy(h.coeff.data(), coefficients, h.coeff.size());
-    DEO_CUDA(cudaStreamSynchronize(rt().stream));   // the old tables may still be in use
+    // No synchronisation and no allocation: the row tables are recomputed on the host (the reference's own row / branch
+    // logic, including the per-row wind direction of upwind operators from sign(c)), written into the pinned arena and sent
+    // to the SAME device blocks with copies ordered on the library stream behind every application already enqueued; the
+    // kernels' parameter blocks are host-side values taken by each launch.
     return finalize_plan(plan);
 }
 

@@ -170,22 +170,10 @@ void upwind_n_right(const OpView<T>& A, RowSink<T>& S) {
 }
 
 template <typename T>
-void* upload(deo_plan* plan, const void* host, size_t bytes, cudaError_t* err) {
-    auto blob = std::make_unique<DeviceBlob>();
-    *err = cudaMalloc(&blob->p, bytes ? bytes : 1);
-    if (*err != cudaSuccess) return nullptr;
-    blob->bytes = bytes;
-    if (bytes) {
-        *err = cudaMemcpy(blob->p, host, bytes, cudaMemcpyHostToDevice);
-        if (*err != cudaSuccess) return nullptr;
-    }
-    void* p = blob->p;
-    plan->blobs.push_back(std::move(blob));
-    return p;
-}
+void* upload(deo_plan* plan, const void* host, size_t bytes, cudaError_t* err) { return plan_upload(plan, host, bytes, err); }
 
 template <typename T>
-int32_t build_op(deo_plan* plan, const HostOp& H, bool bpv, DevOp<T>& D) {
+int32_t build_op(deo_plan* plan, const HostOp& H, bool bpv, DevOp<T>& D, size_t op_index) {
     OpView<T> A(H);
     const bool upwind = H.d.kind == DEO_OP_UPWIND;
     const bool nonuni = H.d.nonuniform != 0;
@@ -288,6 +276,8 @@ int32_t build_op(deo_plan* plan, const HostOp& H, bool bpv, DevOp<T>& D) {
         DEO_REQUIRE(put(i - 1, i), "op on axis %d: low boundary row %d has no stencil", H.d.axis, i);
     for (int i = 1; i <= D.nhigh; ++i)
         DEO_REQUIRE(put(D.nlow + i - 1, n - D.nhigh + i), "op on axis %d: high boundary row %d has no stencil", H.d.axis, n - D.nhigh + i);
+    if (plan->host_brows.size() <= op_index) plan->host_brows.resize(op_index + 1);
+    plan->host_brows[op_index].assign((const unsigned char*)br.data(), (const unsigned char*)br.data() + br.size() * sizeof(BRow<T>));
     cudaError_t e;
     D.brows = (const BRow<T>*)upload<T>(plan, br.data(), br.size() * sizeof(BRow<T>), &e);
     if (!D.brows) return cuda_fail(e, "upload(brows)", __FILE__, __LINE__);
@@ -296,7 +286,6 @@ int32_t build_op(deo_plan* plan, const HostOp& H, bool bpv, DevOp<T>& D) {
 
 template <typename T>
 int32_t build_typed(deo_plan* plan) {
-    plan->blobs.clear();
     plan->devplan.assign(sizeof(DevPlan<T>), 0);
     DevPlan<T>& P = *reinterpret_cast<DevPlan<T>*>(plan->devplan.data());
     P.ndims = plan->ndims;
@@ -343,7 +332,7 @@ int32_t build_typed(deo_plan* plan) {
         // The 1-D L*Q*u path goes through the BoundaryPaddedVector methods (convolutions.jl:367-469);
         // N-D arrays and plain padded vectors go through the AbstractVector methods (:27-118).
         const bool bpv = plan->ndims == 1 && plan->bc[H.d.axis].d.kind != DEO_BC_NONE;
-        int32_t rc = build_op<T>(plan, H, bpv, P.ops[k]);
+        int32_t rc = build_op<T>(plan, H, bpv, P.ops[k], k);
         if (rc) return rc;
     }
     return DEO_OK;
@@ -397,6 +386,39 @@ struct RowGenT final : RowGenerator {
 };
 
 }  // namespace
+
+void* plan_upload(deo_plan* plan, const void* host, size_t bytes, cudaError_t* err) {
+    *err = cudaSuccess;
+    DeviceBlob* b = nullptr;
+    if (plan->blob_cursor < plan->blobs.size() && plan->blobs[plan->blob_cursor]->bytes == bytes) {
+        b = plan->blobs[plan->blob_cursor].get();                  // same position, same size as in the previous build
+    } else {
+        auto blob = std::make_unique<DeviceBlob>();
+        *err = cudaMalloc(&blob->p, bytes ? bytes : 1);
+        if (*err != cudaSuccess) return nullptr;
+        blob->bytes = bytes;
+        b = blob.get();
+        if (plan->blob_cursor < plan->blobs.size()) plan->blobs[plan->blob_cursor] = std::move(blob);   // frees the old one (cudaFree synchronises)
+        else plan->blobs.push_back(std::move(blob));
+    }
+    ++plan->blob_cursor;
+    if (bytes) {
+        const size_t padded = (bytes + 15) / 16 * 16;
+        plan->stage_want += padded;
+        if (plan->stage && plan->stage_used + padded <= plan->stage_cap) {
+            unsigned char* src = plan->stage + plan->stage_used;
+            memcpy(src, host, bytes);
+            plan->stage_used += padded;
+            *err = cudaMemcpyAsync(b->p, src, bytes, cudaMemcpyHostToDevice, rt().stream);   // pinned source: truly asynchronous
+        } else {
+            // no arena yet (first build) or it is too small: pageable source, the runtime stages it itself (and waits for
+            // the stream first); the arena grows before the next rebuild
+            *err = cudaMemcpyAsync(b->p, host, bytes, cudaMemcpyHostToDevice, rt().stream);
+        }
+        if (*err != cudaSuccess) return nullptr;
+    }
+    return b->p;
+}
 
 std::unique_ptr<RowGenerator> make_row_generator(const deo_plan* plan, int k) {
     const HostOp& H = plan->ops[(size_t)k];

@@ -509,6 +509,37 @@ def test_update_coefficients_and_scalar_scaling(D, O):
     assert_close((-2.5 * G) * u, O.apply_axis(B2, u, Qo), np.float64, "scalar * ghost")
 
 
+def test_time_stepping_updates_coefficients_in_place(D, O):
+    """A time-stepping loop with a time-dependent coefficient vector (update_coefficients!, abstract_operator_functions.jl:
+    190-194): one cached plan, refreshed in place each step (no new plans, no device allocations), wind direction of the
+    upwind rows re-selected from sign(c) every time, results equal to the oracle's at every step."""
+    shape = (72, 40, 52)
+    h = tuple(1.0 / (s + 1) for s in shape)
+    dxs = [nonuniform_dx(s, hh, np.float64) for s, hh in zip(shape, h)]
+    rows = np.arange(shape[2])
+    c_of_t = lambda t: np.sin(0.37 * rows + t) * (1 + 0.5 * np.cos(3 * t))       # changes sign pattern from step to step
+    Ux = D.UpwindDifference[3](1, 2, dxs[2], shape[2], c_of_t(0.0))
+    A = D.CenteredDifference[1](2, 4, dxs[0], shape[0]) + D.CenteredDifference[2](2, 4, dxs[1], shape[1]) + Ux
+    Q = D.compose(*D.RobinBC((1.0, 0.5, 0.25), (1.0, -0.5, 0.75), dxs, 1, shape))
+    G = A * Q
+    bcs = {ax + 1: O.RobinBC((1.0, 0.5, 0.25), (1.0, -0.5, 0.75), dxs[ax], 1) for ax in range(3)}
+    u = uniform_field(shape, np.float64, seed=31)
+    ud = D.DeviceArray.from_host(u)
+    dud = D.DeviceArray(shape, np.float64)
+    plans_seen = set()
+    for step in range(6):
+        t = 0.4 * step
+        Ux.set_coefficients(c_of_t(t))
+        D.mul_(dud, G, ud)
+        cache = G.__dict__[D.apply._PLAN_CACHE_ATTR]
+        assert len(cache) == 1
+        plans_seen.add(id(next(iter(cache.values()))[0][0][0]))
+        Bs = [O.CenteredDifference(2, 4, dxs[0], shape[0], axis=1), O.CenteredDifference(2, 4, dxs[1], shape[1], axis=2),
+              O.UpwindDifference(1, 2, dxs[2], shape[2], c_of_t(t), axis=3)]
+        assert_close(dud.to_host(), O.apply_sum(Bs, u, bcs), np.float64, f"step {step}")
+    assert len(plans_seen) == 1, "coefficient updates must refresh the cached plan, not build new ones"
+
+
 def test_host_buffer_path_equals_device_path(D):
     shape = (40, 36, 20)
     h = (0.1, 0.1, 0.1)
