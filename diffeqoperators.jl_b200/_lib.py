@@ -61,6 +61,7 @@ EXPORTS = {
     "deo_buffer_download": [C.c_void_p, C.c_void_p, C.c_size_t],
     "deo_buffer_devptr": [C.c_void_p, C.POINTER(C.c_void_p)],
     "deo_buffer_wrap": [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)],
+    "deo_buffer_muladd": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int32, C.c_int64, C.c_int32],
     "deo_host_alloc": [C.c_size_t, C.POINTER(C.c_void_p)],
     "deo_host_free": [C.c_void_p],
     "deo_plan_create": [C.POINTER(PlanDesc), C.POINTER(C.c_void_p)],

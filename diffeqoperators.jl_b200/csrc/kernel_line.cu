@@ -25,7 +25,7 @@ template <typename T, int R>
 struct LineParams {
     static constexpr int NQ = 2 * R + 1, TB = 2 * R + 2;
     int n, padded, accumulate, table;
-    int K_l, K_r, pad0_, pad1_;
+    int K_l, K_r, periodic, pad1_;   // periodic: 1-D PeriodicBC, ghosts l = u[end], r = u[1] (bc_operators.jl:192)
     T a_l[kLineMaxK], a_r[kLineMaxK];
     T b_l, b_r;
     T w[NQ];
@@ -93,6 +93,7 @@ k_line(const __grid_constant__ LineParams<T, R> S, const T* __restrict__ in, T* 
             if (!(low || high)) continue;
             T g;
             if (S.padded) g = __ldg(in + (high ? n + 1 : 0));
+            else if (S.periodic) g = __ldg(u + (high ? 0 : n - 1));      // the wrap-around read
             else {
                 g = T(0);
                 const int K = high ? S.K_r : S.K_l;
@@ -179,7 +180,9 @@ bool fill_line(deo_plan* plan, std::vector<std::unique_ptr<RowGenerator>>& gens,
         S.tab = (const T*)plan_upload(plan, tabT.data(), tabT.size() * sizeof(T), &e);
         if (!S.tab) { cudaGetLastError(); return false; }
     }
-    if (!S.padded) {
+    if (!S.padded && plan->bc[0].d.kind == DEO_BC_PERIODIC) {
+        S.periodic = 1;
+    } else if (!S.padded) {
         const HostBC& H = plan->bc[0];
         if (H.d.kind != DEO_BC_AFFINE || H.d.per_face || H.d.K_l > kLineMaxK || H.d.K_r > kLineMaxK) return false;
         S.K_l = H.d.K_l; S.K_r = H.d.K_r;
@@ -240,7 +243,7 @@ int32_t launch_line_T(const LineConfig& C, const void* u, void* du, cudaStream_t
 // Attaches a LineConfig when the plan is a 1-D sum of stencils of reach <= 4 with an affine BC (or a pre-padded input).
 int32_t line_configure(deo_plan* plan) {
     if (plan->ndims != 1 || getenv("DEO_NO_LINE")) return DEO_OK;
-    if (!plan->padded[0] && (plan->bc[0].d.kind != DEO_BC_AFFINE || plan->bc[0].d.per_face)) return DEO_OK;
+    if (!plan->padded[0] && plan->bc[0].d.kind != DEO_BC_PERIODIC && (plan->bc[0].d.kind != DEO_BC_AFFINE || plan->bc[0].d.per_face)) return DEO_OK;
     if (plan->dims[0] > (1LL << 30)) return DEO_OK;
     std::vector<std::unique_ptr<RowGenerator>> gens;
     for (size_t k = 0; k < plan->ops.size(); ++k) {

@@ -170,9 +170,35 @@ __global__ void k_axpy_inplace(T* __restrict__ out, const T* __restrict__ u, T d
         out[i] = fma(dt, out[i], u[i]);
 }
 
+// dst[i] = scale * a[i] * b[i] (+ dst[i]): the products of derivative results nonlinear_diffusion! forms
+// (derivative_operator.jl:31-66)
+template <typename T>
+__global__ void k_muladd(T* __restrict__ dst, const T* __restrict__ a, const T* __restrict__ b, T scale, int accumulate, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const T v = scale * (a[i] * b[i]);
+        dst[i] = accumulate ? dst[i] + v : v;
+    }
+}
+
 }  // namespace deo
 
 extern "C" {
+
+int32_t deo_buffer_muladd(deo_buffer* dst, const deo_buffer* a, const deo_buffer* b, double scale, int32_t accumulate, int64_t n, int32_t dtype) {
+    DEO_REQUIRE(dst && a && b && n >= 0, "deo_buffer_muladd: bad arguments");
+    DEO_REQUIRE(dtype == DEO_F32 || dtype == DEO_F64, "deo_buffer_muladd: dtype must be DEO_F32 or DEO_F64");
+    const size_t es = dtype == DEO_F64 ? 8 : 4;
+    DEO_REQUIRE(dst->bytes >= (size_t)n * es && a->bytes >= (size_t)n * es && b->bytes >= (size_t)n * es, "deo_buffer_muladd: buffers shorter than %lld elements", (long long)n);
+    int32_t rc = ensure_init();
+    if (rc) return rc;
+    if (n == 0) return DEO_OK;
+    const unsigned grid = (unsigned)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+    if (dtype == DEO_F64) k_muladd<double><<<grid, 256, 0, rt().stream>>>((double*)dst->ptr, (const double*)a->ptr, (const double*)b->ptr, scale, accumulate, n);
+    else k_muladd<float><<<grid, 256, 0, rt().stream>>>((float*)dst->ptr, (const float*)a->ptr, (const float*)b->ptr, (float)scale, accumulate, n);
+    DEO_CUDA(cudaGetLastError());
+    g_launches += 1;
+    return DEO_OK;
+}
 
 int32_t deo_plan_create(const deo_plan_desc* desc, deo_plan** out) {
     DEO_REQUIRE(out != nullptr, "deo_plan_create: null argument");

@@ -48,6 +48,16 @@ class DeviceArray:
         _lib.check(_lib.load().deo_buffer_wrap(C.c_void_p(devptr), nbytes, C.byref(h)))
         return cls(shape, dtype, handle=h)
 
+    def view(self, offset_elems: int, shape):
+        """Non-owning window of this buffer (column-major): e.g. one component `A[.., n]` of a space-tensor.  The parent
+        must outlive the view."""
+        shape = tuple(int(v) for v in shape)
+        n = int(np.prod(shape, dtype=np.int64))
+        assert 0 <= offset_elems and offset_elems + n <= self.size, "view outside the buffer"
+        v = DeviceArray.wrap(self.devptr + int(offset_elems) * self.dtype.itemsize, shape, self.dtype)
+        v._parent = self
+        return v
+
     def upload(self, a):
         a = np.asfortranarray(a, dtype=self.dtype)
         assert a.shape == self.shape, f"shape mismatch: {a.shape} vs {self.shape}"

@@ -156,6 +156,12 @@ class AbstractDiffEqLinearOperator:
         pass
 
 
+def _compose(L1, L2):
+    """L1 * L2 of two operators = DiffEqOperatorComposition((L2, L1))  (composite_operators.jl:107-115)."""
+    from .vector_calculus import compose_operators
+    return compose_operators(L1, L2)
+
+
 def _base(op):
     return op.L if isinstance(op, GhostDerivativeOperator) else op
 
@@ -230,6 +236,8 @@ class DerivativeOperator(AbstractDiffEqLinearOperator):
         from .apply import mul_alloc
         if isinstance(other, AbstractBC):
             return GhostDerivativeOperator(self, other)       # ghost_derivative_operator.jl:7-9
+        if isinstance(other, AbstractDiffEqLinearOperator):
+            return _compose(self, other)
         return mul_alloc(self, other)                          # derivative_operator_functions.jl:150-163
 
     def update_coefficients_(self, u, p, t):
@@ -399,6 +407,8 @@ class GhostDerivativeOperator(AbstractDiffEqLinearOperator):
 
     def __mul__(self, u):
         from .apply import mul_alloc
+        if isinstance(u, AbstractDiffEqLinearOperator):
+            return _compose(self, u)
         return mul_alloc(self, u)                  # :26-37
 
     def update_coefficients_(self, u, p, t):       # :61-63
@@ -439,6 +449,8 @@ class DiffEqOperatorCombination(AbstractDiffEqLinearOperator):
         if isinstance(other, AbstractBC):
             # (sum L)*Q = sum(L*Q)   ghost_derivative_operator.jl:11-13
             return DiffEqOperatorCombination(tuple(op * other for op in self.ops))
+        if isinstance(other, AbstractDiffEqLinearOperator):
+            return _compose(self, other)
         return mul_alloc(self, other)              # composite_operators.jl:64-65
 
     def update_coefficients_(self, u, p, t):

@@ -120,6 +120,9 @@ int32_t deo_buffer_upload(deo_buffer *dst, const void *host, size_t bytes);     
 int32_t deo_buffer_download(void *host, const deo_buffer *src, size_t bytes);   /* Array(::DeviceArray), synchronises */
 int32_t deo_buffer_devptr(const deo_buffer *buf, void **devptr);                /* raw pointer, e.g. to alias from torch */
 int32_t deo_buffer_wrap(void *devptr, size_t bytes, deo_buffer **out);          /* non-owning view of foreign device memory */
+/* dst[i] = scale * a[i] * b[i] (+ dst[i] when accumulate): the products of derivative results that
+ * nonlinear_diffusion! (derivative_operators/derivative_operator.jl:31-66) sums; first n elements of type dtype. */
+int32_t deo_buffer_muladd(deo_buffer *dst, const deo_buffer *a, const deo_buffer *b, double scale, int32_t accumulate, int64_t n, int32_t dtype);
 int32_t deo_host_alloc(size_t bytes, void **host);                              /* pinned host memory for the host-buffer path */
 int32_t deo_host_free(void *host);
 

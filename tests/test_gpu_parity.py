@@ -131,7 +131,7 @@ def test_config1_heat_equation_1d(D, O):
 def test_line_kernel_selection_and_table_mode(D, O):
     """1-D plans: uniform + constant coefficient -> 'line' (weights in the constant bank); non-uniform grids,
     coefficient vectors, mixed-sign upwind and sums of operators -> 'line-table' (merged per-row weights);
-    PeriodicBC stays on the per-point kernel."""
+    1-D PeriodicBC (l = u[end], r = u[1], bc_operators.jl:192) runs on the line kernel too (wrap-around read)."""
     n = 4099                                                           # odd length: scalar tail stores
     h = 1.0 / (n + 1)
     u = uniform_field(n, np.float64, seed=12)
@@ -150,8 +150,12 @@ def test_line_kernel_selection_and_table_mode(D, O):
         assert D.build_plans(G, (n,), (n,), np.float64)[0][0].info[0] == want_kernel
         want = sum(O.apply_axis(b, u, Qo) for _, b in ops)
         assert_close(G * u, want, np.float64, f"line {want_kernel} {len(ops)} ops")
-    Gp = A3 * D.PeriodicBC(np.float64)
-    assert D.build_plans(Gp, (n,), (n,), np.float64)[0][0].info[0] == "generic"
+    for Ap, Bp in ((A3, B3), (A2, B2)):
+        Gp = Ap * D.PeriodicBC(np.float64)
+        assert D.build_plans(Gp, (n,), (n,), np.float64)[0][0].info[0].startswith("line")
+        assert_close(Gp * u, O.apply_axis(Bp, u, O.PeriodicBC()), np.float64, "line periodic")
+        gen = D.mul_alloc(Gp, D.DeviceArray.from_host(u), flags=D._lib.DEO_FLAG_FORCE_GENERIC).to_host()
+        assert_close(Gp * u, gen, np.float64, "line periodic vs per-point kernel")
     # overwrite = false on the 1-D kernel
     du0 = uniform_field(n, np.float64, seed=13)
     dd = D.DeviceArray.from_host(du0)
