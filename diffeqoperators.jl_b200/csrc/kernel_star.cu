@@ -343,9 +343,11 @@ int32_t star_configure(deo_plan* plan) {
     cfg->v2 = !(getenv("DEO_STAR_V") && atoi(getenv("DEO_STAR_V")) == 1);            // A/B: DEO_STAR_V=1 selects the first-generation kernel
     // march-axis chunk bound: short items re-synchronise the CTAs often (L2 reuse of the shared halo rows) at the price of
     // 2R priming planes each; measured best: 24 planes (3-D) / 16 rows (2-D strips) for the persistent kernel, 32 for the first one
-    cfg->zchunk_max = getenv("DEO_STAR_ZCHUNK") ? atoi(getenv("DEO_STAR_ZCHUNK")) : (cfg->v2 ? (mid ? 24 : 16) : 32);
-    if (cfg->zchunk_max < 1) cfg->zchunk_max = cfg->v2 ? 24 : 32;
+    const int zchunk_default = cfg->v2 ? (mid ? 24 : 16) : 32;
+    cfg->zchunk_max = getenv("DEO_STAR_ZCHUNK") ? atoi(getenv("DEO_STAR_ZCHUNK")) : zchunk_default;
+    if (cfg->zchunk_max < 4 || cfg->zchunk_max > (1 << 20)) cfg->zchunk_max = zchunk_default;   // tuning knobs are clamped, never trusted
     cfg->l2promo = getenv("DEO_TMA_L2PROMO") ? atoi(getenv("DEO_TMA_L2PROMO")) : 3;
+    if (cfg->l2promo < 0 || cfg->l2promo > 3) cfg->l2promo = 3;
     cfg->group = getenv("DEO_STAR_GROUP") ? atoi(getenv("DEO_STAR_GROUP")) : -1;   // measured: the plain order is fastest
     if (getenv("DEO_HALO_TIMEOUT_S") && atof(getenv("DEO_HALO_TIMEOUT_S")) > 0)
         cfg->halo_timeout_ns = (unsigned long long)(atof(getenv("DEO_HALO_TIMEOUT_S")) * 1e9);

@@ -12,6 +12,7 @@ import numpy as np
 
 from . import _lib
 from .apply import Plan, _bc_for_axis, _terms
+from .bc import AffineBC
 from .device import DeviceArray
 
 
@@ -85,8 +86,21 @@ class SlabPlan(Plan):
         nd = len(global_shape)
         bcs = []
         for ax in range(1, nd + 1):
-            qs = [Q for L, Q in terms if L.axis == ax]
-            bcs.append(_bc_for_axis(qs[0], ax, nd) if qs else None)
+            per_op = [_bc_for_axis(Q, ax, nd) for L, Q in terms if L.axis == ax]
+            if not per_op:
+                bcs.append(None)
+                continue
+            if any(b is None for b in per_op):
+                raise AssertionError("slab plans need a boundary condition on every differentiated axis")
+            # every operator of an axis must see the same ghosts (same rule as apply.build_plans): a sum such as
+            # L1*Q1 + L2*Q2 along one axis cannot be fused into one pass
+            first = per_op[0]
+            for b in per_op[1:]:
+                same = b is first or (isinstance(b, AffineBC) and isinstance(first, AffineBC) and np.array_equal(b.a_l, first.a_l) and
+                                      np.array_equal(b.a_r, first.a_r) and b.b_l == first.b_l and b.b_r == first.b_r)
+                if not same:
+                    raise NotImplementedError("operators on one axis with different boundary conditions must be applied separately")
+            bcs.append(first)
         super().__init__([(L, L.axis - 1) for L, _ in terms], bcs, tuple(global_shape), [False] * nd, dtype,
                          flags=flags, dist=ctx._h if ctx is not None else None,
                          local_rank=None if ctx is not None else local_rank)
