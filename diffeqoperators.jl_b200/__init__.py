@@ -14,6 +14,7 @@ from .bc import (RobinBC, GeneralBC, NeumannBC, DirichletBC, Dirichlet0BC, Neuma
 from .device import DeviceArray, zeros, sync
 from .apply import mul_, mul_alloc, step_, Plan, build_plans
 from .vector_calculus import (Gradient, Divergence, Curl, GradientOperator, DivergenceOperator, CurlOperator,
-                              nonlinear_diffusion, nonlinear_diffusion_, DiffEqOperatorComposition, compose_operators)
+                              nonlinear_diffusion, nonlinear_diffusion_, DiffEqOperatorComposition, compose_operators,
+                              concretize, ldiv)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

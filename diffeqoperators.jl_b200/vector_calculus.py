@@ -203,6 +203,40 @@ class DiffEqOperatorComposition(AbstractDiffEqLinearOperator):
         return mul_(y, self.ops[-1], acc)
 
 
+# ---- concretization of L*Q and `\` (ghost_derivative_operator.jl:39-58, concretization.jl:914-958) -----------------------------
+def concretize(G, shape, dtype=None, batch=256):
+    """Array(A::GhostDerivativeOperator, s) -> (A_l, A_b): the linear part (prod(s) x prod(s), column-major unknowns) and
+    the affine part of `u -> (L*Q) u`, obtained ON THE DEVICE by applying the fused plan to zero and to the unit vectors
+    (`A_b = G*0`, `A_l e_k = G*e_k - A_b`); only the columns come back to the host.  Meant for the sizes the reference
+    concretizes (tests, direct solves of small problems): cost is prod(s) applications."""
+    shape = tuple(int(v) for v in np.atleast_1d(shape))
+    T = np.dtype(dtype) if dtype is not None else np.dtype(G.T)
+    n = int(np.prod(shape))
+    e = DeviceArray.from_host(np.zeros(shape, dtype=T, order="F"))
+    out = DeviceArray(shape, T)
+    mul_(out, G, e)
+    A_b = out.to_host().reshape(-1, order="F").astype(T)
+    A_l = np.empty((n, n), dtype=T, order="F")
+    host = np.zeros(n, dtype=T)
+    for k in range(n):
+        host[k] = 1
+        e.upload(host.reshape(shape, order="F"))
+        host[k] = 0
+        mul_(out, G, e)
+        A_l[:, k] = out.to_host().reshape(-1, order="F") - A_b
+    return A_l, A_b
+
+
+def ldiv(G, u):
+    r"""A \ u for A = L*Q: solve A_l x = u - A_b with the concretized operator (ghost_derivative_operator.jl:39-58; the
+    reference factorises the sparse matrix on the CPU, here the matrix comes from the device and LAPACK solves it)."""
+    arr = u.to_host() if isinstance(u, DeviceArray) else np.asarray(u)
+    A_l, A_b = concretize(G, arr.shape, arr.dtype)
+    x = np.linalg.solve(A_l.astype(np.float64), arr.reshape(-1, order="F").astype(np.float64) - A_b)
+    x = np.asfortranarray(x.astype(arr.dtype).reshape(arr.shape, order="F"))
+    return DeviceArray.from_host(x) if isinstance(u, DeviceArray) else x
+
+
 def compose_operators(L1, L2):
     """L1 ∘ L2 (composite_operators.jl:113-115): apply L2, then L1."""
     a = L2.ops if isinstance(L2, DiffEqOperatorComposition) else (L2,)
