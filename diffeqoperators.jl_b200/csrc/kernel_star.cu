@@ -320,19 +320,26 @@ int32_t star_configure(deo_plan* plan) {
     const bool want_v2 = !(getenv("DEO_STAR_V") && atoi(getenv("DEO_STAR_V")) == 1);
     if (plan->accumulate && !want_v2) return DEO_OK;                    // overwrite = false: persistent kernel only
     const size_t es = plan->elem();
-    // Pre-padded input (the ghost layer is part of the array): persistent kernel only, and not along the contiguous axis --
-    // there the input row is shifted by ONE element against the output row, so the 16-byte alignment TMA wants for a box's
-    // first element (a box starting at an odd Float64 index is an illegal instruction) and the 16-byte vector stores of du
-    // cannot both hold.  Such plans stay on the per-point kernel.
-    if (plan->padded[0]) return DEO_OK;
-    for (int a = 0; a < nd; ++a) if (plan->padded[a] && (!want_v2 || plan->slab_axis >= 0)) return DEO_OK;
-    if (((size_t)plan->in_dim(0) * es) % 16 != 0) return DEO_OK;       // TMA: row pitch must be a multiple of 16 bytes
+    // The first-generation kernel needs a tensor map (row pitch a multiple of 16 B) and takes no pre-padded input; the
+    // persistent kernel falls back to cp.async element copies where TMA cannot be used: an odd row pitch, or an input
+    // padded along the contiguous axis (its rows are shifted by ONE element against the rows of du: a TMA box starting at
+    // an odd Float64 index is an illegal instruction).  Slab plans keep the tensor-map path.
+    const bool pitch_ok = ((size_t)plan->in_dim(0) * es) % 16 == 0;
+    const bool need_loader = !pitch_ok || plan->padded[0];
+    bool any_padded = false;
+    for (int a = 0; a < nd; ++a) any_padded = any_padded || plan->padded[a];
+    if ((need_loader || any_padded) && (!want_v2 || plan->slab_axis >= 0)) return DEO_OK;
     const bool mid = nd == 3;
     const int kaxis[3] = {0, mid ? 1 : 2, mid ? 2 : -1};                 // plan axis -> kernel axis (x, mid, march)
     const int paxis[3] = {0, mid ? 1 : -1, mid ? 2 : 1};                 // kernel axis -> plan axis
     auto cfg = std::make_shared<StarConfig>();
     cfg->mid = mid;
     cfg->accumulate = plan->accumulate != 0;
+    cfg->loader = need_loader;
+    cfg->scalar_io = ((size_t)plan->dims[0] * es) % 16 != 0;              // rows of du not 16-byte aligned
+    cfg->in_dims[0] = (int)plan->in_dim(0);
+    cfg->in_dims[1] = mid ? (int)plan->in_dim(1) : 1;
+    cfg->in_dims[2] = (int)plan->in_dim(nd - 1);
     cfg->sm_count = rt().sm_count;
     const char* env_py = getenv("DEO_STAR_PY");
     cfg->py = env_py ? atoi(env_py) : 2;                    // 2 rows per thread, two CTAs per SM measured fastest on B200
@@ -418,8 +425,10 @@ int32_t launch_star(const deo_plan* plan, void* du, const void* u, long long z0,
     StarConfig& C = *static_cast<StarConfig*>(plan->star.get());
     PFN_encodeTiled enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return DEO_ERR_CUDA; }
-    DEO_REQUIRE((reinterpret_cast<uintptr_t>(u) & 15) == 0 && (reinterpret_cast<uintptr_t>(du) & 15) == 0,
+    DEO_REQUIRE((C.loader || (reinterpret_cast<uintptr_t>(u) & 15) == 0) && (C.scalar_io || (reinterpret_cast<uintptr_t>(du) & 15) == 0),
                 "star kernel: buffers must be 16-byte aligned");
+    DEO_REQUIRE((reinterpret_cast<uintptr_t>(u) % plan->elem()) == 0 && (reinterpret_cast<uintptr_t>(du) % plan->elem()) == 0,
+                "star kernel: buffers must be aligned to their element type");
     // tensor map over the input field: (nx, ny, nz_in) for 3-D, (nx, 1, ny_in) for 2-D
     const size_t es = plan->elem();
     const bool mid = C.mid;
@@ -438,7 +447,7 @@ int32_t launch_star(const deo_plan* plan, void* du, const void* u, long long z0,
     const int promo_env = C.l2promo;
     const CUtensorMapL2promotion promo = promo_env == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo_env == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
                                          : promo_env == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
-    CUresult r = enc(&C.tmap, es == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(u), dims,
+    CUresult r = C.loader ? CUDA_SUCCESS : enc(&C.tmap, es == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(u), dims,
                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return DEO_ERR_CUDA; }
@@ -469,7 +478,7 @@ StarLimits star_limits(const deo_plan* plan) {
     StarLimits L;
     if (!plan->star) return L;
     const StarConfig& C = *static_cast<const StarConfig*>(plan->star.get());
-    L.fusable = C.mid && C.zchunk_max > 0;
+    L.fusable = C.mid && C.zchunk_max > 0 && !C.loader;
     L.min_fused_planes = 3LL * C.zchunk_max + 4 * C.R + 4;                 // at least 3 chunks whatever the chunk search picks (it only shortens chunks)
     return L;
 }

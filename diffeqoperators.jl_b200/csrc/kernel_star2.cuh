@@ -32,6 +32,9 @@ struct Star2Launch {
     unsigned long long timeout_ns;
     int stagger_ns;                  // experiment: CTA b starts b * stagger_ns late
     int pace_cycles;                 // experiment: minimum SM cycles between two plane issues of a CTA
+    int loader;                      // 0: TMA tensor map; 1: cp.async element copies by the helper warps (any row pitch / element offset)
+    int scalar_io;                   // du rows are not 16-byte aligned: element-wise global loads / stores of du
+    int in_nx, in_ny, in_nz;         // input extents (loader == 1: bounds of the element copies)
     int ns;                          // ring slots in use
     int st_cs, ld_policy;            // cache hints: streaming stores of du; TMA loads of u with L2 evict_last (1) / evict_first (2)
     unsigned long long* trace;       // debug (DEO_STAR2_TRACE): per item {first plane issued (ns), last plane issued (ns), SM id}
@@ -101,6 +104,28 @@ __device__ __forceinline__ void tma_load_3d_hint(void* dst, const CUtensorMap* m
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(dst)),
         "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
         : "memory");
+}
+
+// Global loads / stores of one vector of du: 16-byte accesses, or element by element (the first `nvalid` ones) when the
+// rows of du are not 16-byte aligned (row length not a multiple of the vector).
+template <typename T, int N>
+__device__ __forceinline__ void gld(const T* p, T (&out)[N], int nvalid, bool scalar) {
+    if (!scalar) { ld_vec<T, N>(p, out); return; }
+#pragma unroll
+    for (int v = 0; v < N; ++v) out[v] = v < nvalid ? p[v] : T(0);
+}
+template <typename T, int N>
+__device__ __forceinline__ void gst(T* p, const T (&in)[N], int nvalid, bool scalar) {
+    if (!scalar) { st_vec<T, N>(p, in); return; }
+#pragma unroll
+    for (int v = 0; v < N; ++v) if (v < nvalid) p[v] = in[v];
+}
+template <typename T>
+__device__ __forceinline__ void cp_async_elem(T* dst, const T* src, bool inb) {
+    const uint32_t d = smem_u32(dst);
+    const int sz = inb ? (int)sizeof(T) : 0;             // src-size 0: the destination is zero-filled, the source is not read
+    if constexpr (sizeof(T) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
 }
 
 // f(false_type, integral_constant<int, U>) for U = 0 .. N-1, leaving early (returns true) as soon as stop() holds
@@ -290,6 +315,77 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
     if (warp >= NW) {
         // ============================== helper warpgroup (warps NW .. NW+3) ==============================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(G::REGS_HELPER));
+        if (L.loader) {
+            // ---- generic-alignment mode: no tensor map (row pitch not a multiple of 16 B, or an input shifted by one element
+            // against the output: pre-padded contiguous axis).  The four helper warps are equal workers: a ring slot belongs to
+            // worker slot % 4, which waits for the slot to be released, copies the plane element by element with cp.async
+            // (zero-fill outside the array), evaluates its ghost-touching rows and arrives on `fixed`.  Warp NW's lane 0 also
+            // hands out the work items, two ahead of its own progress.
+            const int me = warp - NW;
+            int published = 0, next_item = blockIdx.x;
+            bool sentinel = false;
+            auto publish = [&]() {
+                if (sentinel) return;
+                const bool last = next_item >= L.n_items;
+                itemq[published % G::NIQ] = last ? -1 : next_item;
+                mbar_arrive_u32(item_u32 + 8u * (published % G::NIQ));
+                ++published;
+                if (last) sentinel = true;
+                else next_item = (int)gridDim.x + (int)atomicAdd(L.sched, 1u);
+            };
+            if (me == 0 && lane == 0) { publish(); publish(); }
+            int g = 0;
+#pragma unroll 1
+            for (int q = 0;; ++q) {
+                mbar_wait_u32(item_u32 + 8u * (q % G::NIQ), (q / G::NIQ) & 1);
+                const int item = itemq[q % G::NIQ];
+                if (item < 0) break;
+                if (me == 0 && lane == 0) publish();
+                const Star2Item I = star2_item<G::TX, G::TY, MID>(L, item);
+                const int n = I.zc1 - I.zc0 + 2 * R;
+                const bool f_xlo = has_x && I.tx0 == 0, f_xhi = has_x && I.tx0 + G::TX >= nx;
+                const bool f_ylo = has_y && I.ty0 == 0, f_yhi = has_y && I.ty0 + G::TY >= ny;
+                const bool face = f_xlo || f_xhi || f_ylo || f_yhi;
+#pragma unroll 1
+                for (int k = 0; k < n; ++k, ++g) {
+                    const int slot = g % ns;
+                    if (slot % 4 != me) continue;
+                    if (g >= ns) mbar_wait_u32(empty_u32 + 8u * slot, ((g / ns) - 1) & 1);
+                    T* pl = planes + (size_t)slot * PLANE_ELEMS;
+                    const int pz = I.zc0 - R + k + S.in_off_z;
+                    const bool z_in = pz >= 0 && pz < L.in_nz;
+                    const T* zbase = u + (long long)pz * S.isz;
+                    constexpr int NEL = MID ? G::PITCH * G::ROWS : G::PITCH;
+#pragma unroll 1
+                    for (int idx = lane; idx < NEL; idx += 32) {
+                        const int r = MID ? idx / PITCH : 0, c = idx - r * PITCH;
+                        const int xi = I.tx0 - HX + c + S.in_off_x, yi = MID ? I.ty0 - R + r + S.in_off_y : 0;
+                        const bool inb = z_in && xi >= 0 && xi < L.in_nx && yi >= 0 && yi < L.in_ny;
+                        cp_async_elem<T>(pl + idx, inb ? zbase + ((long long)xi + (long long)yi * S.isy) : u, inb);
+                    }
+                    asm volatile("cp.async.wait_all;" ::: "memory");
+                    __syncwarp();
+                    if (face && k >= R && k < n - R) {
+                        const int gzp = I.zc0 - R + k + S.row0_z;
+                        if constexpr (has_x) {
+                            if (f_xlo) star2_fix_x<T, R, MID, 0>(S, pl, I.tx0, I.ty0, nx, ny, ex, lane, gzp);
+                            if (f_xhi) star2_fix_x<T, R, MID, 1>(S, pl, I.tx0, I.ty0, nx, ny, ex, lane, gzp);
+                        }
+                        if constexpr (has_y) {
+                            if (f_ylo) star2_fix_y<T, R, 0>(S, pl, I.tx0, I.ty0, nx, ny, ey, lane, gzp);
+                            if (f_yhi) star2_fix_y<T, R, 1>(S, pl, I.tx0, I.ty0, nx, ny, ey, lane, gzp);
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_u32(fixed_u32 + 8u * slot);
+                }
+            }
+            if (me == 0 && lane == 0) {
+                __threadfence();
+                if (atomicAdd(L.sched + 1, 1u) == gridDim.x - 1) { L.sched[0] = 0u; L.sched[1] = 0u; __threadfence(); }
+            }
+            return;
+        }
         if (warp == NW) {
             // ---- producer: one elected lane keeps the TMA ring full, across item boundaries ----------------
             if (lane != 0) return;
@@ -436,37 +532,44 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
         if (item < 0) break;
         const Star2Item I = star2_item<G::TX, G::TY, MID>(L, item);
         const int tx0 = I.tx0, ty0 = I.ty0, zc0 = I.zc0, zc1 = I.zc1;
-        const int n_planes = zc1 - zc0 + 2 * R;
-        int gx[PY], gy[PY], soff[PY];
+        // Per-item state is kept small (the register queue needs the registers): the PY vectors of a thread sit at a constant
+        // distance from the first one, in shared memory (SOFF_J) and in du (row stride in 3-D, a constant in 2-D strips).
+        constexpr int SOFF_J = MID ? PITCH : NW * 32 * VEC;
+        int gx[PY], gy[PY], nv[MID ? 1 : PY];                  // nv: elements of the vector inside the array (3-D: the rows share x)
         bool live[PY];
-        T* ocur[PY];                                          // output pointer of each vector at the centre plane of the current step
+        int soff0;
+        T* ocur0;                                             // output pointer of the first vector at the centre plane of the current step
+        auto soff_of = [&](int j) { return soff0 + j * SOFF_J; };
+        auto ocur_of = [&](int j) { return MID ? ocur0 + (long long)j * S.osy : ocur0 + j * SOFF_J; };
 #pragma unroll
         for (int j = 0; j < PY; ++j) {
             if constexpr (MID) {
                 gx[j] = tx0 + lane * VEC;
                 gy[j] = ty0 + wy * PY + j;
-                soff[j] = (R + wy * PY + j) * PITCH + HX + lane * VEC;
+                if (j == 0) soff0 = (R + wy * PY) * PITCH + HX + lane * VEC;
             } else {
                 const int seg = (j * NW + wy) * 32 + lane;
                 gx[j] = tx0 + seg * VEC;
                 gy[j] = 0;
-                soff[j] = HX + seg * VEC;
+                if (j == 0) soff0 = HX + seg * VEC;
             }
+            nv[MID ? 0 : j] = min(VEC, nx - gx[j]);
             live[j] = gx[j] < nx && gy[j] < ny;
-            ocur[j] = du + (long long)gx[j] + (long long)gy[j] * S.osy + (long long)zc0 * S.osz;
+            if (j == 0) ocur0 = du + (long long)gx[0] + (long long)gy[0] * S.osy + (long long)zc0 * S.osz;
         }
         // which of this thread's values come from the helper's evaluation (bit v: element v of the vector)
         const bool xlo_tile = has_x && tx0 == 0, xhi_tile = has_x && tx0 + G::TX >= nx;
         const bool ylo_tile = has_y && ty0 == 0, yhi_tile = has_y && ty0 + G::TY >= ny;
         const bool xface = xlo_tile || xhi_tile, yface = ylo_tile || yhi_tile;
-        int xsel[PY], xoff[PY], ysel[PY];
+        int xsel[MID ? 1 : PY], xoff[MID ? 1 : PY], ysel[PY];  // 3-D: the PY rows of a thread share x
 #pragma unroll
         for (int j = 0; j < PY; ++j) {
-            xsel[j] = 0; xoff[j] = 0; ysel[j] = 0;
+            if (!MID || j == 0) { xsel[MID ? 0 : j] = 0; xoff[MID ? 0 : j] = 0; }
+            ysel[j] = 0;
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
-                if (xlo_tile && gx[j] + v < ex) { xsel[j] |= 1 << v; xoff[j] = -HX; }
-                if (xhi_tile && gx[j] + v >= nx - ex && gx[j] + v < nx) { xsel[j] |= 1 << v; xoff[j] = HX; }
+                if (xlo_tile && gx[j] + v < ex) { xsel[MID ? 0 : j] |= 1 << v; xoff[MID ? 0 : j] = -HX; }
+                if (xhi_tile && gx[j] + v >= nx - ex && gx[j] + v < nx) { xsel[MID ? 0 : j] |= 1 << v; xoff[MID ? 0 : j] = HX; }
             }
             if (ylo_tile && gy[j] < ey) ysel[j] = -R * PITCH;
             if (yhi_tile && gy[j] >= ny - ey && gy[j] < ny) ysel[j] = R * PITCH;
@@ -513,7 +616,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
 #pragma unroll
             for (int j = 0; j < PY; ++j) {
                 T val[VEC];
-                ld_vec<T, VEC>(pn + soff[j], val);
+                ld_vec<T, VEC>(pn + soff_of(j), val);
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) zq[j][v][k + 1] = val[v];
             }
@@ -525,7 +628,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
         }
         int slot_c = slot_a - R;                               // centre plane of the first step = R planes behind
         if (slot_c < 0) slot_c += ns;
-        int z = zc0, ka = 2 * R;
+        int z = zc0;
 
         // One step = acquire plane z+R, compute and store centre plane z.  ROT = u >= 0: the new plane overwrites
         // physical queue slot u, logical tap t lives in physical slot (u + 1 + t) % NQ (NQ consecutive steps u = 0..NQ-1
@@ -542,7 +645,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
 #pragma unroll
                 for (int j = 0; j < PY; ++j) {
                     T val[VEC];
-                    ld_vec<T, VEC>(pn + soff[j], val);
+                    ld_vec<T, VEC>(pn + soff_of(j), val);
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) {
                         if constexpr (ROT < 0) {
@@ -554,7 +657,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                         }
                     }
                 }
-                if (ka >= n_planes - R) {                      // planes past the chunk only feed the queue: free the slot now
+                if (z >= zc1 - R) {                            // planes past the chunk only feed the queue: free the slot now
                     __syncwarp();
                     if (lane == 0) mbar_arrive_u32(empty_u32 + 8u * slot_a);
                 }
@@ -571,7 +674,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                 T xw[PY][XW];
 #pragma unroll
                 for (int j = 0; j < PY; ++j) {
-                    load_x_halo<T, R>(pl + soff[j], xw[j]);
+                    load_x_halo<T, R>(pl + soff_of(j), xw[j]);
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) { xw[j][R + v] = zq[j][v][P(R)]; tot[j][v] = T(0); }
                 }
@@ -588,7 +691,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
 #pragma unroll
                 for (int j = 0; j < PY; ++j) {
                     T xw[XW];
-                    load_x_halo<T, R>(pl + soff[j], xw);
+                    load_x_halo<T, R>(pl + soff_of(j), xw);
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) xw[R + v] = zq[j][v][P(R)];
 #pragma unroll
@@ -607,11 +710,11 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                 if (xface) {
 #pragma unroll
                     for (int j = 0; j < PY; ++j) {
-                        if (xsel[j] != 0) {
+                        if (xsel[MID ? 0 : j] != 0) {
                             T f[VEC];
-                            ld_vec<T, VEC>(pl + soff[j] + xoff[j], f);
+                            ld_vec<T, VEC>(pl + soff_of(j) + xoff[MID ? 0 : j], f);
 #pragma unroll
-                            for (int v = 0; v < VEC; ++v) if ((xsel[j] >> v) & 1) tot[j][v] = f[v];
+                            for (int v = 0; v < VEC; ++v) if ((xsel[MID ? 0 : j] >> v) & 1) tot[j][v] = f[v];
                         }
                     }
                 }
@@ -630,7 +733,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
 #pragma unroll
                         for (int v = 0; v < VEC; ++v) row[v] = zq[r - R][v][P(R)];
                     } else {
-                        ld_vec<T, VEC>(pl + soff[0] + (r - R) * PITCH, row);
+                        ld_vec<T, VEC>(pl + soff0 + (r - R) * PITCH, row);
                     }
 #pragma unroll
                     for (int j = 0; j < PY; ++j) {
@@ -646,7 +749,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                 if (yface) {
 #pragma unroll
                     for (int j = 0; j < PY; ++j)
-                        if (ysel[j] != 0) ld_vec<T, VEC>(pl + soff[j] + ysel[j], acc[j]);   // warp-uniform: a tile row belongs to one warp
+                        if (ysel[j] != 0) ld_vec<T, VEC>(pl + soff_of(j) + ysel[j], acc[j]);   // warp-uniform: a tile row belongs to one warp
                 }
 #pragma unroll
                 for (int j = 0; j < PY; ++j)
@@ -680,7 +783,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                         for (int j = 0; j < PY; ++j) {
 #pragma unroll
                             for (int v = 0; v < VEC; ++v) { pk[j][v] = T(0); if (!(has_x || has_y)) tot[j][v] = T(0); }
-                            if (live[j]) ld_vec<T, VEC>(ocur[j], pk[j]);
+                            if (live[j]) gld<T, VEC>(ocur_of(j), pk[j], nv[MID ? 0 : j], L.scalar_io);
                         }
                     }
                 } else if (!(has_x || has_y)) {            // low edge row of a march-axis-only plan: its term arrives later
@@ -703,7 +806,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                     T base[VEC];
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) base[v] = T(0);
-                    if (L.accumulate && !parked) ld_vec<T, VEC>(ocur[j], base);   // a parked term already contains the old du
+                    if (L.accumulate && !parked) gld<T, VEC>(ocur_of(j), base, nv[MID ? 0 : j], L.scalar_io);   // a parked term already contains the old du
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) {
                         if (L.axpy) base[v] += zq[j][v][P(R)];
@@ -721,7 +824,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
             }
 #pragma unroll
             for (int j = 0; j < PY; ++j)
-                if (live[j]) { if (L.st_cs) st_vec_cs<T, VEC>(ocur[j], tot[j]); else st_vec<T, VEC>(ocur[j], tot[j]); }
+                if (live[j]) { if (L.st_cs) st_vec_cs<T, VEC>(ocur_of(j), tot[j]); else gst<T, VEC>(ocur_of(j), tot[j], nv[MID ? 0 : j], L.scalar_io); }
 
             if constexpr (has_z && EDGE) {
                 // --- march-axis rows that touch a ghost, from the register queue -------------------------------
@@ -753,9 +856,9 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                         }
 #pragma unroll 1
                         for (int r = 0; r < ez; ++r) {
-                            T* dst = ocur[j] + (long long)(r - S.row0_z - z) * S.osz;
+                            T* dst = ocur_of(j) + (long long)(r - S.row0_z - z) * S.osz;
                             T old[VEC];
-                            ld_vec<T, VEC>(dst, old);
+                            gld<T, VEC>(dst, old, nv[MID ? 0 : j], L.scalar_io);
 #pragma unroll
                             for (int v = 0; v < VEC; ++v) {
                                 T s = fma_t(S.bw[2][0][r][0], gl[v], T(0));
@@ -763,7 +866,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                                 for (int kk = 1; kk < TB; ++kk) s = fma_t(S.bw[2][0][r][kk], zq[j][v][kk - 1], s);
                                 old[v] = L.axpy ? fma_t((T)L.dt, s, old[v]) : old[v] + s;
                             }
-                            st_vec<T, VEC>(dst, old);
+                            gst<T, VEC>(dst, old, nv[MID ? 0 : j], L.scalar_io);
                         }
                     }
                 }
@@ -796,7 +899,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                         }
 #pragma unroll 1
                         for (int r = 0; r < ez; ++r) {
-                            T* dst = ocur[j] + (long long)(S.nglob_z - ez + r - S.row0_z - z) * S.osz;
+                            T* dst = ocur_of(j) + (long long)(S.nglob_z - ez + r - S.row0_z - z) * S.osz;
                             T out[VEC];
 #pragma unroll
                             for (int v = 0; v < VEC; ++v) {
@@ -809,21 +912,21 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                                 T prev[VEC];
 #pragma unroll
                                 for (int v = 0; v < VEC; ++v) prev[v] = T(0);
-                                if (L.accumulate) ld_vec<T, VEC>(dst, prev);
+                                if (L.accumulate) gld<T, VEC>(dst, prev, nv[MID ? 0 : j], L.scalar_io);
 #pragma unroll
                                 for (int v = 0; v < VEC; ++v) out[v] = fma_t(L.axpy ? (T)L.dt : T(1), out[v], prev[v]);
                             }
-                            st_vec<T, VEC>(dst, out);
+                            gst<T, VEC>(dst, out, nv[MID ? 0 : j], L.scalar_io);
                         }
                     }
                 }
             }
             // --- advance the ring and the output pointers ---------------------------------------------------
-            ++z; ++ka;
+            ++z;
             if (++slot_a == ns) { slot_a = 0; par_a ^= 1; }
             if (++slot_c == ns) slot_c = 0;
 #pragma unroll
-            for (int j = 0; j < PY; ++j) ocur[j] += S.osz;
+            ocur0 += S.osz;
         };
 
         // Step ranges of this item: [zc0, z_lo) edge steps next to the low march-axis face (global planes 0..R),
@@ -921,6 +1024,9 @@ int32_t launch_variant2(const StarConfig& C, const void* u, void* du, long long 
     // Prefetch depth: R + 6 ring slots (R + 1 live planes, 5 in flight).  Deeper rings only lengthen the queues in the
     // memory system: the CTAs drift further apart and the halo rows / columns neighbouring tiles share fall out of L2
     // before the second reader arrives (measured on 1024^3: 11 slots 330, 8 slots 354 Gpoints/s).
+    Lp.loader = C.loader ? 1 : 0;
+    Lp.scalar_io = C.scalar_io ? 1 : 0;
+    Lp.in_nx = C.in_dims[0]; Lp.in_ny = C.in_dims[1]; Lp.in_nz = C.in_dims[2];
     Lp.ns = G::NS < R + 6 ? G::NS : R + 6;
     if (getenv("DEO_STAR2_NS")) { const int v = atoi(getenv("DEO_STAR2_NS")); if (v >= R + 4 && v <= G::NS) Lp.ns = v; }
     Lp.trace = nullptr;

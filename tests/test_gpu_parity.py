@@ -384,21 +384,17 @@ def test_tiled_kernel_takes_prepadded_perface_and_periodic_inputs(D, O, dtype):
     for shape, a in [((200, 70, 37), 4), ((136, 44, 30), 6), ((264, 90), 4)]:
         nd = len(shape)
         h = tuple(1.0 / (s + 1) for s in shape)
-        # --- pre-padded input along every axis but the contiguous one: each operator reads its own axis' ghost layer of M
-        # (padding along dim 1 shifts rows by one element against du -- no 16-byte alignment for TMA -- and stays per-point)
+        # --- pre-padded composite: each operator reads its own axis' ghost layer of M (the contiguous axis included: its
+        # rows are shifted by one element against du, so the kernel loads with cp.async element copies instead of TMA)
         pairs = [make_pair("centered", 2, a, h[ax - 1], shape[ax - 1], axis=ax, dtype=dtype) for ax in range(1, nd + 1)]
-        mshape = [shape[0]] + [s + 2 for s in shape[1:]]
-        M = uniform_field(mshape, dtype, seed=21)
-        A = pairs[1][0]
-        for pr in pairs[2:]:
+        M = uniform_field([s + 2 for s in shape], dtype, seed=21)
+        A = pairs[0][0]
+        for pr in pairs[1:]:
             A = A + pr[0]
         du = np.zeros(shape, dtype=dtype, order="F")
         D.mul_(du, A, M)
         assert _kernel_of(D, A, shape, M.shape, dtype).startswith("star"), "pre-padded input must run tiled"
-        assert_close(du, O.apply_sum([pr[1] for pr in pairs[1:]], M, None), dtype, f"pre-padded {shape}")
-        A = pairs[0][0]
-        for pr in pairs[1:]:
-            A = A + pr[0]
+        assert_close(du, O.apply_sum([pr[1] for pr in pairs], M, None), dtype, f"pre-padded {shape}")
         # --- N-D periodic
         u = uniform_field(shape, dtype, seed=22)
         Qp = D.compose(*D.PeriodicBC(dtype, shape))
@@ -429,6 +425,33 @@ def test_tiled_kernel_takes_prepadded_perface_and_periodic_inputs(D, O, dtype):
     G = A * D.compose(*Qd)
     assert _kernel_of(D, G, shape, shape, dtype).startswith("star"), "per-pencil BC arrays must run tiled"
     assert_close(G * u, O.apply_sum([pr[1] for pr in pairs], u, Qo), dtype, "per-pencil BC tables, 3 axes")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_tiled_kernel_takes_any_row_length(D, O, dtype):
+    """Row lengths that are not a multiple of 16 bytes (no tensor map possible): cp.async element copies into the same
+    shared-memory layout, element-wise stores of du.  Includes the reference's own 51^3 example
+    (test/DerivativeOperators/3D_laplacian.jl:3-20: CenteredDifference(2,2) on 51^3 with Dirichlet0 faces)."""
+    for shape, a, bc in [((51, 51, 51), 2, "dirichlet0"), ((67, 45, 33), 4, "robin"), ((131, 70, 29), 6, "robin"), ((333, 41), 4, "robin"),
+                         ((2051, 37), 2, "robin")]:
+        nd = len(shape)
+        h = tuple(1.0 / (s + 1) for s in shape)
+        A, Bs = _laplacian_pair(shape, a, h, dtype)
+        if bc == "dirichlet0":
+            Q = D.compose(*D.Dirichlet0BC(dtype, shape))
+            bcs = {ax + 1: O.Dirichlet0BC(dtype) for ax in range(nd)}
+        else:
+            Q = D.compose(*D.RobinBC((1.0, 0.5, 0.25), (1.0, -0.5, 0.75), h, 1, shape, dtype=dtype))
+            bcs = {ax + 1: O.RobinBC((1.0, 0.5, 0.25), (1.0, -0.5, 0.75), h[ax], 1, dtype) for ax in range(nd)}
+        u = uniform_field(shape, dtype, seed=41)
+        G = A * Q
+        assert _kernel_of(D, G, shape, shape, dtype).startswith("star"), f"{shape} must run tiled"
+        want = O.apply_sum(Bs, u, bcs)
+        assert_close(G * u, want, dtype, f"odd row length {shape}")
+        ud = D.DeviceArray.from_host(u)
+        acc = D.DeviceArray.from_host(u)
+        D.mul_(acc, G, ud, overwrite=False)                      # element-wise read-modify-write of du
+        assert np.abs(acc.to_host().astype(np.float64) - (u.astype(np.float64) + want)).max() <= TOL[np.dtype(dtype)] * np.abs(want).max()
 
 
 def test_periodic_nd_quirk(D, O):
