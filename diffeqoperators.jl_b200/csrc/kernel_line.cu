@@ -43,13 +43,10 @@ template <> struct LVec<double> { using type = double2; static constexpr int N =
 template <> struct LVec<float> { using type = float4; static constexpr int N = 4; };
 
 template <typename T, int R, bool TABLE>
-__global__ void __launch_bounds__(256)
-k_line(const __grid_constant__ LineParams<T, R> S, const T* __restrict__ in, T* __restrict__ du) {
+__device__ __forceinline__ void line_vector(const LineParams<T, R>& S, const T* __restrict__ in, T* __restrict__ du, long long x0) {
     constexpr int VEC = LVec<T>::N, NQ = 2 * R + 1, TB = 2 * R + 2;
     using V = typename LVec<T>::type;
     const int n = S.n;
-    const long long x0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
-    if (x0 >= n) return;
     const T* u = in + (S.padded ? 1 : 0);                 // u[j] = q[j+1]
     // window u[x0-R .. x0+VEC-1+R], clamped loads (clamped values are only used by rows that are recomputed below)
     T xw[VEC + 2 * R];
@@ -123,6 +120,25 @@ k_line(const __grid_constant__ LineParams<T, R> S, const T* __restrict__ in, T* 
         *reinterpret_cast<V*>(du + x0) = o;
     } else {
         for (int v = 0; v < VEC && x0 + v < n; ++v) du[x0 + v] = S.accumulate ? du[x0 + v] + out[v] : out[v];
+    }
+}
+
+// VPT vectors per thread, a whole grid apart (coalesced): their loads are independent, so a thread has VPT times the bytes in
+// flight -- the 1-D application is ~3 us of L2-resident traffic and latency-bound, not bandwidth-bound.
+template <typename T, int R, bool TABLE, int VPT>
+__global__ void __launch_bounds__(256)
+k_line(const __grid_constant__ LineParams<T, R> S, const T* __restrict__ in, T* __restrict__ du) {
+    constexpr int VEC = LVec<T>::N;
+    const long long stride = (long long)gridDim.x * blockDim.x * VEC;
+    const long long x0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    // Programmatic dependent launch: let the next application's CTAs be scheduled while this one runs, and wait -- before
+    // the first global access -- until the previous one has completed and flushed.  No-ops without the launch attribute.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+        const long long x = x0 + k * stride;
+        if (x < S.n) line_vector<T, R, TABLE>(S, in, du, x);
     }
 }
 
@@ -219,10 +235,26 @@ int32_t launch_line_R(const LineConfig& C, const void* u, void* du, cudaStream_t
     const LineParams<T, R>& S = *reinterpret_cast<const LineParams<T, R>*>(C.params.data());
     constexpr int VEC = LVec<T>::N;
     const long long threads = ((long long)S.n + VEC - 1) / VEC;
-    const unsigned grid = (unsigned)((threads + 255) / 256);
-    if (S.table) k_line<T, R, true><<<grid, 256, 0, s>>>(S, (const T*)u, (T*)du);
-    else k_line<T, R, false><<<grid, 256, 0, s>>>(S, (const T*)u, (T*)du);
-    DEO_CUDA(cudaGetLastError());
+    constexpr int block = 256;
+    static const int vpt = [] {                           // vectors per thread (DEO_LINE_VPT: 1, 2 or 4)
+        const char* e = getenv("DEO_LINE_VPT");
+        const int v = e ? atoi(e) : 1;                    // measured on B200, N = 1e6: 1 -> 3.01 us, 2 -> 3.45 us, 4 -> 3.26 us per application
+        return (v == 1 || v == 2 || v == 4) ? v : 1;
+    }();
+    const unsigned grid = (unsigned)((threads + (long long)block * vpt - 1) / ((long long)block * vpt));
+    static const bool pdl = getenv("DEO_LINE_PDL") && atoi(getenv("DEO_LINE_PDL")) == 1;   // measured: no gain (3.03 vs 3.01 us), off by default
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    const T* up = (const T*)u;
+    T* dup = (T*)du;
+#define DEO_LINE_LAUNCH(TAB, V) DEO_CUDA(cudaLaunchKernelEx(&cfg, k_line<T, R, TAB, V>, S, up, dup))
+    if (S.table) { if (vpt == 1) DEO_LINE_LAUNCH(true, 1); else if (vpt == 2) DEO_LINE_LAUNCH(true, 2); else DEO_LINE_LAUNCH(true, 4); }
+    else { if (vpt == 1) DEO_LINE_LAUNCH(false, 1); else if (vpt == 2) DEO_LINE_LAUNCH(false, 2); else DEO_LINE_LAUNCH(false, 4); }
+#undef DEO_LINE_LAUNCH
     return DEO_OK;
 }
 
