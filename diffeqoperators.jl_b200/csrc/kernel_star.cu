@@ -270,7 +270,11 @@ bool fill_params_R(const deo_plan* plan, const int kaxis[3], bool mid, StarConfi
 }  // namespace
 
 Star2Runtime& star2_rt() {
-    static Star2Runtime r;
+    // one set of words per device (deo_init may select another device later in the same process)
+    static Star2Runtime per_device[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    Star2Runtime& r = per_device[dev >= 0 && dev < 64 ? dev : 0];
     if (!r.err_host) {
         if (cudaHostAlloc((void**)&r.err_host, sizeof(int), cudaHostAllocMapped) == cudaSuccess &&
             cudaHostGetDevicePointer((void**)&r.err_dev, r.err_host, 0) == cudaSuccess) {

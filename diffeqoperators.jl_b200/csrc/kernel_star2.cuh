@@ -20,6 +20,12 @@
 #pragma once
 #include "kernel_star.cuh"
 
+// TABLE variants on 3-D tiles: x-axis weights of a thread's own points in registers up to this radius, in shared memory
+// above it (the register queue of the larger radii leaves no room)
+#ifndef STAR2_WXREG_MID_R
+#define STAR2_WXREG_MID_R 0
+#endif
+
 namespace deo {
 
 struct Star2Launch {
@@ -126,6 +132,43 @@ __device__ __forceinline__ void cp_async_elem(T* dst, const T* src, bool inb) {
     const int sz = inb ? (int)sizeof(T) : 0;             // src-size 0: the destination is zero-filled, the source is not read
     if constexpr (sizeof(T) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
     else asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+
+// acc[v] = fma(w[v] or w, x[v], acc[v]) over the VEC points of a thread.  Float32 on sm_100 has a packed two-lane FMA
+// (fma.rn.f32x2, FFMA2 in SASS: two IEEE FMAs per issue slot, same rounding as two scalar ones); the Float32 variants of this
+// kernel are issue-bound (65 % issue active, 38 % FMA pipe on C3), so halving the FMA instruction count is what moves them.
+#ifndef STAR2_FFMA2
+#define STAR2_FFMA2 1
+#endif
+__device__ __forceinline__ void fma2_f32(float& a0, float& a1, float w0, float w1, float x0, float x1) {
+    asm("{\n"
+        ".reg .b64 ra, rw, rx;\n"
+        "mov.b64 ra, {%0, %1};\n"
+        "mov.b64 rw, {%2, %3};\n"
+        "mov.b64 rx, {%4, %5};\n"
+        "fma.rn.f32x2 ra, rw, rx, ra;\n"
+        "mov.b64 {%0, %1}, ra;\n"
+        "}" : "+f"(a0), "+f"(a1) : "f"(w0), "f"(w1), "f"(x0), "f"(x1));
+}
+template <typename T, int N>
+__device__ __forceinline__ void fma_row(T (&acc)[N], T w, const T (&x)[N]) {
+    if constexpr (STAR2_FFMA2 && std::is_same<T, float>::value && N == 4) {
+        fma2_f32(acc[0], acc[1], w, w, x[0], x[1]);
+        fma2_f32(acc[2], acc[3], w, w, x[2], x[3]);
+    } else {
+#pragma unroll
+        for (int v = 0; v < N; ++v) acc[v] = fma_t(w, x[v], acc[v]);
+    }
+}
+template <typename T, int N>
+__device__ __forceinline__ void fma_row_w(T (&acc)[N], const T (&w)[N], const T (&x)[N]) {
+    if constexpr (STAR2_FFMA2 && std::is_same<T, float>::value && N == 4) {
+        fma2_f32(acc[0], acc[1], w[0], w[1], x[0], x[1]);
+        fma2_f32(acc[2], acc[3], w[2], w[3], x[2], x[3]);
+    } else {
+#pragma unroll
+        for (int v = 0; v < N; ++v) acc[v] = fma_t(w[v], x[v], acc[v]);
+    }
 }
 
 // f(false_type, integral_constant<int, U>) for U = 0 .. N-1, leaving early (returns true) as soon as stop() holds
@@ -576,11 +619,12 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
         }
         // TABLE, 2-D strips: the x-axis weights of this thread's own points stay in registers for the whole item
         // (3-D tiles stage them in shared memory, see below: registers are what the 2.5-D queue needs)
-        constexpr bool WXREG = TABLE && has_x && !MID;
-        T wx[WXREG ? PY : 1][WXREG ? VEC : 1][WXREG ? NQ : 1];
+        constexpr bool WXREG = TABLE && has_x && (!MID || STAR2_WXREG_MID_R >= R);
+        constexpr int WXJ = MID ? 1 : PY;                         // 3-D: the PY rows of a thread share x
+        T wx[WXREG ? WXJ : 1][WXREG ? VEC : 1][WXREG ? NQ : 1];
         if constexpr (WXREG) {
 #pragma unroll
-            for (int j = 0; j < PY; ++j)
+            for (int j = 0; j < WXJ; ++j)
 #pragma unroll
                 for (int v = 0; v < VEC; ++v)
 #pragma unroll
@@ -593,7 +637,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
         const T* sWx = sWz + G::TAB_ZMAX * NQ;                // [NQ][TX]: tap-major, so that a lane's VEC weights of one tap are one 16-byte load
         if constexpr (TABLE) {
             T* wbuf = tabbuf + (q & 1) * G::TAB_ELEMS;
-            if constexpr (has_x && MID) {
+            if constexpr (has_x && MID && !WXREG) {
                 for (int i = threadIdx.x; i < G::TX * NQ; i += NW * 32)
                     wbuf[(G::TY + G::TAB_ZMAX) * NQ + (i % NQ) * G::TX + i / NQ] = __ldg(S.tab[0] + (long long)min(tx0 + i / NQ, nx - 1) * NQ + i % NQ);
             }
@@ -669,7 +713,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
             T pk[EDGE ? PY : 1][EDGE ? VEC : 1];               // EDGE: march-axis term of a high-face row, parked in du earlier
             bool parked = false;
             // ================= x operator: window = [R halo | VEC own (already in the queue) | R halo] =================
-            if constexpr (has_x && TABLE && MID) {
+            if constexpr (has_x && TABLE && MID && !WXREG) {
                 // per-point weights from shared memory, one 16-byte load per tap shared by the PY rows (same x)
                 T xw[PY][XW];
 #pragma unroll
@@ -683,9 +727,12 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                     T wv[VEC];
                     ld_vec<T, VEC>(sWx + t * G::TX + lane * VEC, wv);
 #pragma unroll
-                    for (int j = 0; j < PY; ++j)
+                    for (int j = 0; j < PY; ++j) {
+                        T xs[VEC];
 #pragma unroll
-                        for (int v = 0; v < VEC; ++v) tot[j][v] = fma_t(wv[v], xw[j][v + t], tot[j][v]);
+                        for (int v = 0; v < VEC; ++v) xs[v] = xw[j][v + t];
+                        fma_row_w<T, VEC>(tot[j], wv, xs);
+                    }
                 }
             } else if constexpr (has_x) {
 #pragma unroll
@@ -695,14 +742,20 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) xw[R + v] = zq[j][v][P(R)];
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) {
-                        T a = T(0);
+                    for (int v = 0; v < VEC; ++v) tot[j][v] = T(0);
 #pragma unroll
-                        for (int t = 0; t < NQ; ++t) {
-                            if constexpr (TABLE) a = fma_t(wx[j][v][t], xw[v + t], a);
-                            else a = fma_t(S.w[0][t], xw[v + t], a);
+                    for (int t = 0; t < NQ; ++t) {                    // per point still the taps in ascending order
+                        T xs[VEC];
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) xs[v] = xw[v + t];
+                        if constexpr (TABLE) {
+                            T ws[VEC];
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) ws[v] = wx[MID ? 0 : j][v][t];
+                            fma_row_w<T, VEC>(tot[j], ws, xs);
+                        } else {
+                            fma_row<T, VEC>(tot[j], S.w[0][t], xs);
                         }
-                        tot[j][v] = a;
                     }
                 }
             }
@@ -741,8 +794,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                         if (t >= 0 && t < NQ) {
                             T wyt;
                             if constexpr (TABLE) wyt = sWy[(wy * PY + j) * NQ + t]; else wyt = S.w[1][t];
-#pragma unroll
-                            for (int v = 0; v < VEC; ++v) acc[j][v] = fma_t(wyt, row[v], acc[j][v]);
+                            fma_row<T, VEC>(acc[j], wyt, row);
                         }
                     }
                 }
@@ -768,13 +820,18 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                     }
 #pragma unroll
                     for (int j = 0; j < PY; ++j) {
+                        T sz[VEC];
 #pragma unroll
-                        for (int v = 0; v < VEC; ++v) {
-                            T s = T(0);
+                        for (int v = 0; v < VEC; ++v) sz[v] = T(0);
 #pragma unroll
-                            for (int t = 0; t < NQ; ++t) s = fma_t(wz[t], zq[j][v][P(t)], s);
-                            tot[j][v] = (has_x || has_y) ? tot[j][v] + s : s;
+                        for (int t = 0; t < NQ; ++t) {                // per point still the taps in ascending order
+                            T xs[VEC];
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) xs[v] = zq[j][v][P(t)];
+                            fma_row<T, VEC>(sz, wz[t], xs);
                         }
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) tot[j][v] = (has_x || has_y) ? tot[j][v] + sz[v] : sz[v];
                     }
                 } else if (z_high_edge) {                  // the term was parked in du when the queue held its planes
                     if constexpr (EDGE) {
