@@ -361,7 +361,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
         if (L.loader) {
             // ---- generic-alignment mode: no tensor map (row pitch not a multiple of 16 B, or an input shifted by one element
             // against the output: pre-padded contiguous axis).  The four helper warps are equal workers: a ring slot belongs to
-            // worker slot % 4, which waits for the slot to be released, copies the plane element by element with cp.async
+            // worker slot % 4, which waits for the slot to be released, copies the plane row by row with element-wise cp.async
             // (zero-fill outside the array), evaluates its ghost-touching rows and arrives on `fixed`.  Warp NW's lane 0 also
             // hands out the work items, two ahead of its own progress.
             const int me = warp - NW;
@@ -389,6 +389,20 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                 const bool f_xlo = has_x && I.tx0 == 0, f_xhi = has_x && I.tx0 + G::TX >= nx;
                 const bool f_ylo = has_y && I.ty0 == 0, f_yhi = has_y && I.ty0 + G::TY >= ny;
                 const bool face = f_xlo || f_xhi || f_ylo || f_yhi;
+                // per item: this lane's clamped source column of every 32-column chunk, and which of them lie inside the array
+                constexpr int NCH = (PITCH + 31) / 32;
+                static_assert(NCH <= 32 || !MID, "column mask");
+                const int x0 = I.tx0 - HX + S.in_off_x, y0 = MID ? I.ty0 - R + S.in_off_y : 0;
+                int coff[MID ? NCH : 1];
+                unsigned xin = 0;
+                if constexpr (MID) {
+#pragma unroll
+                    for (int w = 0; w < NCH; ++w) {
+                        const int xi = x0 + w * 32 + lane;
+                        coff[w] = min(max(xi, 0), L.in_nx - 1);
+                        if (xi >= 0 && xi < L.in_nx) xin |= 1u << w;
+                    }
+                }
 #pragma unroll 1
                 for (int k = 0; k < n; ++k, ++g) {
                     const int slot = g % ns;
@@ -397,14 +411,32 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                     T* pl = planes + (size_t)slot * PLANE_ELEMS;
                     const int pz = I.zc0 - R + k + S.in_off_z;
                     const bool z_in = pz >= 0 && pz < L.in_nz;
-                    const T* zbase = u + (long long)pz * S.isz;
-                    constexpr int NEL = MID ? G::PITCH * G::ROWS : G::PITCH;
+                    // Row by row, 32 columns per instruction; every copy of the plane is in flight before the single wait.  Source
+                    // addresses are clamped into the array (column offsets once per item, row / plane indices per row), so the
+                    // inner loop is one address add and the copy; copies outside the array zero-fill (src-size 0).
+                    const T* gplane = u + (long long)min(max(pz, 0), L.in_nz - 1) * S.isz;
+                    if constexpr (MID) {
+                        const T* grow = gplane + (long long)min(max(y0, 0), L.in_ny - 1) * S.isy;
+                        T* srow = pl + lane;
 #pragma unroll 1
-                    for (int idx = lane; idx < NEL; idx += 32) {
-                        const int r = MID ? idx / PITCH : 0, c = idx - r * PITCH;
-                        const int xi = I.tx0 - HX + c + S.in_off_x, yi = MID ? I.ty0 - R + r + S.in_off_y : 0;
-                        const bool inb = z_in && xi >= 0 && xi < L.in_nx && yi >= 0 && yi < L.in_ny;
-                        cp_async_elem<T>(pl + idx, inb ? zbase + ((long long)xi + (long long)yi * S.isy) : u, inb);
+                        for (int r = 0; r < G::ROWS; ++r) {
+                            const int yi = y0 + r;
+                            const bool row_in = z_in && yi >= 0 && yi < L.in_ny;
+#pragma unroll
+                            for (int w = 0; w < NCH; ++w) {
+                                if (NCH * 32 == PITCH || w * 32 + lane < PITCH)
+                                    cp_async_elem<T>(srow + w * 32, grow + coff[w], row_in && ((xin >> w) & 1u));
+                            }
+                            srow += PITCH;
+                            if (yi >= 0 && yi < L.in_ny - 1) grow += S.isy;
+                        }
+                    } else {                                   // 2-D strip: one long row per plane
+#pragma unroll 1
+                        for (int c = lane; c < PITCH; c += 32) {
+                            const int xi = x0 + c;
+                            const bool inb = z_in && xi >= 0 && xi < L.in_nx;
+                            cp_async_elem<T>(pl + c, inb ? gplane + xi : u, inb);
+                        }
                     }
                     asm volatile("cp.async.wait_all;" ::: "memory");
                     __syncwarp();
@@ -982,7 +1014,6 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
             ++z;
             if (++slot_a == ns) { slot_a = 0; par_a ^= 1; }
             if (++slot_c == ns) slot_c = 0;
-#pragma unroll
             ocur0 += S.osz;
         };
 

@@ -1,11 +1,11 @@
 #!/bin/bash
 # A/B builds of the tiled kernel: tools/ab_build.sh NAME "-DSTAR2_X=1 ..." [radii, default "1 2 3 4"]
-# recompiles the k_star2 instantiation units (and kernel_star.cu) with the extra defines into gpurun_ab/NAME/ and links
-# them with the other objects of csrc/build/ into gpurun_ab/NAME/libdeo_b200.so (copied to ab/NAME.so, which travels to the GPU box; select it with DEO_LIB_PATH).
+# recompiles the k_star2 instantiation units (and kernel_star.cu) with the extra defines into /tmp/deo_ab/NAME/ and links
+# them with the other objects of csrc/build/ into /tmp/deo_ab/NAME/libdeo_b200.so (copied to ab/NAME.so, which travels to the GPU box; select it with DEO_LIB_PATH).
 set -e
 cd "$(dirname "$0")/.."
 NAME=$1; DEFS=$2; RADII=${3:-"1 2 3 4"}
-OUT=gpurun_ab/$NAME; mkdir -p $OUT
+OUT=/tmp/deo_ab/$NAME; mkdir -p $OUT
 CS=diffeqoperators.jl_b200/csrc
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --expt-relaxed-constexpr -Xcompiler -fPIC"
 pids=()
