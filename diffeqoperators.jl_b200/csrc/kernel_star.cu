@@ -298,6 +298,25 @@ bool star_take_halo_timeout() {
     return false;
 }
 
+// Shifted tile origins (input padded along the contiguous axis, see star_configure): tiles start at x = tile * TX - xshift
+// with xshift = 1 (mod the vector length), so that every box of u starts on a 16-byte boundary.  Among those shifts take
+// the one with the fewest tile columns whose first and last tile both keep at least a boundary stencil's width of columns
+// inside the array (a row length that is a multiple of TX needs one more tile column whatever the shift).
+static void choose_xshift(const deo_plan* plan, StarConfig& cfg, bool mid) {
+    if (cfg.xshift == 0) return;
+    const int VEC = (int)(16 / plan->elem());
+    const int nwy = cfg.v2 ? 16 : cfg.nwy, py = cfg.v2 ? 2 : cfg.py;
+    const long long TX = mid ? 32 * VEC : 32 * VEC * nwy * py, nx = plan->dims[0];
+    const long long wmin = 2 * cfg.R + 2;
+    long long best = -1, best_tiles = 0;
+    for (long long sh = 1; sh < TX; sh += VEC) {
+        const long long tiles = (nx + sh + TX - 1) / TX, wlast = (nx - 1 + sh) % TX + 1, wfirst = tiles > 1 ? TX - sh : nx;
+        if (wlast < wmin || wfirst < wmin) continue;
+        if (best < 0 || tiles < best_tiles) { best = sh; best_tiles = tiles; }
+    }
+    cfg.xshift = best > 0 ? (int)best : 1;                   // no admissible shift: tile_fits rejects the plan
+}
+
 // The tile geometry must contain everything the x / y edge paths read (boundary stencils and BC stencils).
 static bool tile_fits(const deo_plan* plan, const StarConfig& cfg, bool mid) {
     const size_t es = plan->elem();
@@ -306,9 +325,10 @@ static bool tile_fits(const deo_plan* plan, const StarConfig& cfg, bool mid) {
     const int nwy = cfg.v2 ? 16 : cfg.nwy, py = cfg.v2 ? 2 : cfg.py;
     const int TX = mid ? 32 * VEC : 32 * VEC * nwy * py, TY = nwy * py;
     const long long nx = plan->dims[0], ny = mid ? plan->dims[1] : 1;
-    const int wlast = (int)((nx - 1) % TX) + 1, hlast = (int)((ny - 1) % TY) + 1;
+    const int wlast = (int)((nx - 1 + cfg.xshift) % TX) + 1, hlast = (int)((ny - 1) % TY) + 1;
     const int Kx = plan->bc[0].d.K_r, Ky = mid ? plan->bc[1].d.K_r : 0;
     if ((cfg.mask & 1) && (wlast + HXh < TB - 1 || wlast + HXh < Kx || nx < TB)) return false;
+    if ((cfg.mask & 1) && cfg.xshift > 0 && nx > TX - cfg.xshift && TX - cfg.xshift < TB) return false;   // shifted first tile too narrow
     if (mid && (cfg.mask & 2) && (hlast + R < TB - 1 || hlast + R < Ky || ny < TB)) return false;
     return true;
 }
@@ -324,12 +344,15 @@ int32_t star_configure(deo_plan* plan) {
     const bool want_v2 = !(getenv("DEO_STAR_V") && atoi(getenv("DEO_STAR_V")) == 1);
     if (plan->accumulate && !want_v2) return DEO_OK;                    // overwrite = false: persistent kernel only
     const size_t es = plan->elem();
-    // The first-generation kernel needs a tensor map (row pitch a multiple of 16 B) and takes no pre-padded input; the
-    // persistent kernel falls back to cp.async element copies where TMA cannot be used: an odd row pitch, or an input
-    // padded along the contiguous axis (its rows are shifted by ONE element against the rows of du: a TMA box starting at
-    // an odd Float64 index is an illegal instruction).  Slab plans keep the tensor-map path.
+    // The first-generation kernel needs a tensor map (row pitch a multiple of 16 B) and takes no pre-padded input.  The
+    // persistent kernel falls back to cp.async element copies where no tensor map exists (odd row pitch).  An input padded
+    // along the contiguous axis has its rows ONE element behind the rows of du, and a TMA box must start on a 16-byte
+    // boundary (an odd Float64 start index is an illegal instruction): the tile origins are shifted by one element instead
+    // (tiles start at x = -1), which puts every box of u on a boundary and leaves the vectors of du misaligned -- du is
+    // then read / written element-wise.  Slab plans keep the plain tensor-map path.
     const bool pitch_ok = ((size_t)plan->in_dim(0) * es) % 16 == 0;
-    const bool need_loader = !pitch_ok || plan->padded[0];
+    const bool need_loader = !pitch_ok || (plan->padded[0] && getenv("DEO_STAR2_NO_XSHIFT") != nullptr);
+    const int xshift = (plan->padded[0] && !need_loader) ? 1 : 0;
     bool any_padded = false;
     for (int a = 0; a < nd; ++a) any_padded = any_padded || plan->padded[a];
     if ((need_loader || any_padded) && (!want_v2 || plan->slab_axis >= 0)) return DEO_OK;
@@ -340,7 +363,8 @@ int32_t star_configure(deo_plan* plan) {
     cfg->mid = mid;
     cfg->accumulate = plan->accumulate != 0;
     cfg->loader = need_loader;
-    cfg->scalar_io = ((size_t)plan->dims[0] * es) % 16 != 0;              // rows of du not 16-byte aligned
+    cfg->xshift = xshift;
+    cfg->scalar_io = ((size_t)plan->dims[0] * es) % 16 != 0 || xshift != 0;   // rows (or, with shifted tiles, vectors) of du not 16-byte aligned
     cfg->in_dims[0] = (int)plan->in_dim(0);
     cfg->in_dims[1] = mid ? (int)plan->in_dim(1) : 1;
     cfg->in_dims[2] = (int)plan->in_dim(nd - 1);
@@ -373,11 +397,16 @@ int32_t star_configure(deo_plan* plan) {
         R = R > h.d.stencil_length / 2 ? R : h.d.stencil_length / 2;
     }
     if (R < 1 || R > 4) const_ok = false;
+    if (getenv("DEO_STAR_DEBUG")) fprintf(stderr, "[star_configure] const_ok=%d nops=%zu R=%d\n", (int)const_ok, plan->ops.size(), R);
     if (const_ok) {
         if (plan->slab_axis >= 0 && plan->slab_count < 3 * R + 3) return DEO_OK;
         cfg->R = R;
         cfg->mask = 0;
         const bool ok = plan->dtype == DEO_F64 ? fill_params_R<double>(plan, kaxis, mid, *cfg) : fill_params_R<float>(plan, kaxis, mid, *cfg);
+        if (ok) choose_xshift(plan, *cfg, mid);
+        if (getenv("DEO_STAR_DEBUG"))
+            fprintf(stderr, "[star_configure] CONST: filled=%d tile_fits=%d R=%d mask=%d xshift=%d dims=%lld x %lld\n", (int)ok, ok ? (int)tile_fits(plan, *cfg, mid) : -1,
+                    R, cfg->mask, cfg->xshift, (long long)plan->dims[0], (long long)plan->dims[1]);
         if (ok && tile_fits(plan, *cfg, mid)) {
             for (const HostOp& h : plan->ops) if (h.d.axis == nd - 1) cfg->nedge_march = h.d.stencil_length / 2;
             plan->star = cfg;
@@ -418,6 +447,7 @@ int32_t star_configure(deo_plan* plan) {
     const size_t cursor0 = plan->blob_cursor;
     const bool ok = plan->dtype == DEO_F64 ? fill_params_table_R<double>(plan, axes, paxis, mid, *cfg)
                                            : fill_params_table_R<float>(plan, axes, paxis, mid, *cfg);
+    if (ok) choose_xshift(plan, *cfg, mid);
     if (!ok || !tile_fits(plan, *cfg, mid)) { plan->blob_cursor = cursor0; return DEO_OK; }
     cfg->nedge_march = (cfg->mask & 4) ? R : 0;
     plan->star = cfg;

@@ -38,6 +38,8 @@ struct Star2Launch {
     unsigned long long timeout_ns;
     int stagger_ns;                  // experiment: CTA b starts b * stagger_ns late
     int pace_cycles;                 // experiment: minimum SM cycles between two plane issues of a CTA
+    int xshift;                      // tile origins along x are tile * TX - xshift: an input padded along the contiguous axis (rows one element
+                                     // behind the rows of du) then starts every TMA box on a 16-byte boundary; du is accessed element-wise
     int loader;                      // 0: TMA tensor map; 1: cp.async element copies by the helper warps (any row pitch / element offset)
     int scalar_io;                   // du rows are not 16-byte aligned: element-wise global loads / stores of du
     int in_nx, in_ny, in_nz;         // input extents (loader == 1: bounds of the element copies)
@@ -113,18 +115,19 @@ __device__ __forceinline__ void tma_load_3d_hint(void* dst, const CUtensorMap* m
 }
 
 // Global loads / stores of one vector of du: 16-byte accesses, or element by element (the first `nvalid` ones) when the
-// rows of du are not 16-byte aligned (row length not a multiple of the vector).
+// rows of du are not 16-byte aligned (row length not a multiple of the vector) or the tile origins are shifted (elements
+// vfirst .. nvalid-1 of the vector lie inside the array).
 template <typename T, int N>
-__device__ __forceinline__ void gld(const T* p, T (&out)[N], int nvalid, bool scalar) {
+__device__ __forceinline__ void gld(const T* p, T (&out)[N], int vfirst, int nvalid, bool scalar) {
     if (!scalar) { ld_vec<T, N>(p, out); return; }
 #pragma unroll
-    for (int v = 0; v < N; ++v) out[v] = v < nvalid ? p[v] : T(0);
+    for (int v = 0; v < N; ++v) out[v] = (v >= vfirst && v < nvalid) ? p[v] : T(0);
 }
 template <typename T, int N>
-__device__ __forceinline__ void gst(T* p, const T (&in)[N], int nvalid, bool scalar) {
+__device__ __forceinline__ void gst(T* p, const T (&in)[N], int vfirst, int nvalid, bool scalar) {
     if (!scalar) { st_vec<T, N>(p, in); return; }
 #pragma unroll
-    for (int v = 0; v < N; ++v) if (v < nvalid) p[v] = in[v];
+    for (int v = 0; v < N; ++v) if (v >= vfirst && v < nvalid) p[v] = in[v];
 }
 template <typename T>
 __device__ __forceinline__ void cp_async_elem(T* dst, const T* src, bool inb) {
@@ -209,7 +212,7 @@ __device__ __forceinline__ Star2Item star2_item(const Star2Launch& L, int it) {
         if (L.fused) chunk += 1;
     }
     Star2Item I;
-    I.tx0 = (tile % L.tiles_x) * TX;
+    I.tx0 = (tile % L.tiles_x) * TX - L.xshift;
     I.ty0 = MID ? (tile / L.tiles_x) * TY : 0;
     I.zc0 = L.z_begin + chunk * L.zchunk;
     I.zc1 = min(I.zc0 + L.zchunk, L.z_end);
@@ -221,7 +224,7 @@ __device__ __forceinline__ Star2Item star2_item(const Star2Launch& L, int it) {
 // over the taps in ascending q order, exactly like the per-point kernel (bitwise equal results).
 //
 // x: lane <-> tile row.  The value of x = i (low) is parked HX columns to the left of its owner, i.e. in local column i;
-//    the value of x = nx-ex+i (high) HX columns to the right of its owner.  Those cells hold nothing but the TMA's
+//    (column i - tx0 when the tile origins are shifted); the value of x = nx-ex+i (high) HX columns to the right of its owner.  Those cells hold nothing but the TMA's
 //    out-of-bounds zeros on a face tile.
 template <typename T, int R, bool MID, int SIDE>
 __device__ __forceinline__ void star2_fix_x(const StarParams<T, R>& S, T* pl, int tx0, int ty0, int nx, int ny, int ex, int lane, int gzp) {
@@ -259,7 +262,7 @@ __device__ __forceinline__ void star2_fix_x(const StarParams<T, R>& S, T* pl, in
                 T res = T(0);
 #pragma unroll
                 for (int kk = 0; kk < TB; ++kk) res = fma_t(S.bw[0][SIDE][i][kk], q[kk], res);
-                if (!SIDE) rowl[i] = res;
+                if (!SIDE) rowl[i - tx0] = res;
                 else rowl[(nx - ex + i) - tx0 + 2 * HX] = res;
             }
         }
@@ -281,7 +284,7 @@ __device__ __forceinline__ void star2_fix_y(const StarParams<T, R>& S, T* pl, in
     } else if (S.per_face[1]) {                          // one BC per boundary pencil: faces column-major over (x, march)
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-            const long long face = (long long)min(tx0 + lane * VEC + v, nx - 1) + (long long)nx * gzp;
+            const long long face = (long long)min(max(tx0 + lane * VEC + v, 0), nx - 1) + (long long)nx * gzp;
             const T* a = (SIDE ? S.pf_a_r[1] : S.pf_a_l[1]) + face * K;
 #pragma unroll 1
             for (int kk = 0; kk < K; ++kk) gh[v] = fma_t(__ldg(a + kk), colbase[((SIDE ? ny - K : 0) + kk) * PITCH + v], gh[v]);
@@ -386,7 +389,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                 if (me == 0 && lane == 0) publish();
                 const Star2Item I = star2_item<G::TX, G::TY, MID>(L, item);
                 const int n = I.zc1 - I.zc0 + 2 * R;
-                const bool f_xlo = has_x && I.tx0 == 0, f_xhi = has_x && I.tx0 + G::TX >= nx;
+                const bool f_xlo = has_x && I.tx0 <= 0, f_xhi = has_x && I.tx0 + G::TX >= nx;
                 const bool f_ylo = has_y && I.ty0 == 0, f_yhi = has_y && I.ty0 + G::TY >= ny;
                 const bool face = f_xlo || f_xhi || f_ylo || f_yhi;
                 // per item: this lane's clamped source column of every 32-column chunk, and which of them lie inside the array
@@ -554,7 +557,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
             if (item < 0) break;
             const Star2Item I = star2_item<G::TX, G::TY, MID>(L, item);
             const int n = I.zc1 - I.zc0 + 2 * R;
-            const bool f_xlo = has_x && I.tx0 == 0, f_xhi = has_x && I.tx0 + G::TX >= nx;
+            const bool f_xlo = has_x && I.tx0 <= 0, f_xhi = has_x && I.tx0 + G::TX >= nx;
             const bool f_ylo = has_y && I.ty0 == 0, f_yhi = has_y && I.ty0 + G::TY >= ny;
             const bool face = f_xlo || f_xhi || f_ylo || f_yhi;
 #pragma unroll 1
@@ -611,6 +614,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
         // distance from the first one, in shared memory (SOFF_J) and in du (row stride in 3-D, a constant in 2-D strips).
         constexpr int SOFF_J = MID ? PITCH : NW * 32 * VEC;
         int gx[PY], gy[PY], nv[MID ? 1 : PY];                  // nv: elements of the vector inside the array (3-D: the rows share x)
+        int vf[MID ? 1 : PY];                                  // first element of the vector inside the array (> 0 only in a shifted first tile)
         bool live[PY];
         int soff0;
         T* ocur0;                                             // output pointer of the first vector at the centre plane of the current step
@@ -629,11 +633,12 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                 if (j == 0) soff0 = HX + seg * VEC;
             }
             nv[MID ? 0 : j] = min(VEC, nx - gx[j]);
+            vf[MID ? 0 : j] = max(0, -gx[j]);
             live[j] = gx[j] < nx && gy[j] < ny;
             if (j == 0) ocur0 = du + (long long)gx[0] + (long long)gy[0] * S.osy + (long long)zc0 * S.osz;
         }
         // which of this thread's values come from the helper's evaluation (bit v: element v of the vector)
-        const bool xlo_tile = has_x && tx0 == 0, xhi_tile = has_x && tx0 + G::TX >= nx;
+        const bool xlo_tile = has_x && tx0 <= 0, xhi_tile = has_x && tx0 + G::TX >= nx;
         const bool ylo_tile = has_y && ty0 == 0, yhi_tile = has_y && ty0 + G::TY >= ny;
         const bool xface = xlo_tile || xhi_tile, yface = ylo_tile || yhi_tile;
         int xsel[MID ? 1 : PY], xoff[MID ? 1 : PY], ysel[PY];  // 3-D: the PY rows of a thread share x
@@ -660,7 +665,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
 #pragma unroll
                 for (int v = 0; v < VEC; ++v)
 #pragma unroll
-                    for (int t = 0; t < NQ; ++t) wx[j][v][t] = __ldg(S.tab[0] + (long long)min(gx[j] + v, nx - 1) * NQ + t);
+                    for (int t = 0; t < NQ; ++t) wx[j][v][t] = __ldg(S.tab[0] + (long long)min(max(gx[j] + v, 0), nx - 1) * NQ + t);
         }
         // TABLE: the mid-axis rows of this tile and the march-axis rows of this chunk are staged in shared memory by the
         // compute warps (double-buffered per item: a warp can only be one item ahead of the slowest one, see the barrier)
@@ -671,7 +676,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
             T* wbuf = tabbuf + (q & 1) * G::TAB_ELEMS;
             if constexpr (has_x && MID && !WXREG) {
                 for (int i = threadIdx.x; i < G::TX * NQ; i += NW * 32)
-                    wbuf[(G::TY + G::TAB_ZMAX) * NQ + (i % NQ) * G::TX + i / NQ] = __ldg(S.tab[0] + (long long)min(tx0 + i / NQ, nx - 1) * NQ + i % NQ);
+                    wbuf[(G::TY + G::TAB_ZMAX) * NQ + (i % NQ) * G::TX + i / NQ] = __ldg(S.tab[0] + (long long)min(max(tx0 + i / NQ, 0), nx - 1) * NQ + i % NQ);
             }
             if constexpr (has_y) {
                 for (int i = threadIdx.x; i < G::TY * NQ; i += NW * 32)
@@ -872,7 +877,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                         for (int j = 0; j < PY; ++j) {
 #pragma unroll
                             for (int v = 0; v < VEC; ++v) { pk[j][v] = T(0); if (!(has_x || has_y)) tot[j][v] = T(0); }
-                            if (live[j]) gld<T, VEC>(ocur_of(j), pk[j], nv[MID ? 0 : j], L.scalar_io);
+                            if (live[j]) gld<T, VEC>(ocur_of(j), pk[j], vf[MID ? 0 : j], nv[MID ? 0 : j], L.scalar_io);
                         }
                     }
                 } else if (!(has_x || has_y)) {            // low edge row of a march-axis-only plan: its term arrives later
@@ -895,7 +900,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                     T base[VEC];
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) base[v] = T(0);
-                    if (L.accumulate && !parked) gld<T, VEC>(ocur_of(j), base, nv[MID ? 0 : j], L.scalar_io);   // a parked term already contains the old du
+                    if (L.accumulate && !parked) gld<T, VEC>(ocur_of(j), base, vf[MID ? 0 : j], nv[MID ? 0 : j], L.scalar_io);   // a parked term already contains the old du
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) {
                         if (L.axpy) base[v] += zq[j][v][P(R)];
@@ -913,7 +918,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
             }
 #pragma unroll
             for (int j = 0; j < PY; ++j)
-                if (live[j]) { if (L.st_cs) st_vec_cs<T, VEC>(ocur_of(j), tot[j]); else gst<T, VEC>(ocur_of(j), tot[j], nv[MID ? 0 : j], L.scalar_io); }
+                if (live[j]) { if (L.st_cs && !L.scalar_io) st_vec_cs<T, VEC>(ocur_of(j), tot[j]); else gst<T, VEC>(ocur_of(j), tot[j], vf[MID ? 0 : j], nv[MID ? 0 : j], L.scalar_io); }
 
             if constexpr (has_z && EDGE) {
                 // --- march-axis rows that touch a ghost, from the register queue -------------------------------
@@ -929,9 +934,9 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                         for (int v = 0; v < VEC; ++v) {
                             T s = T(0);
                             if (S.padded[2]) {              // pre-padded input: the ghost plane is the array's first plane
-                                s = __ldg(u + (long long)(gx[j] + v + S.in_off_x) + (long long)(gy[j] + S.in_off_y) * S.isy);
+                                s = __ldg(u + (long long)(max(gx[j] + v, 0) + S.in_off_x) + (long long)(gy[j] + S.in_off_y) * S.isy);
                             } else if (S.per_face[2]) {     // one BC per boundary pencil: faces column-major over (x, mid)
-                                const long long face = (long long)(gx[j] + v) + (long long)nx * gy[j];
+                                const long long face = (long long)min(max(gx[j] + v, 0), nx - 1) + (long long)nx * gy[j];
                                 const T* a = S.pf_a_l[2] + face * S.K_l[2];
 #pragma unroll
                                 for (int m = 0; m < NQ; ++m) if (m < S.K_l[2]) s = fma_t(__ldg(a + m), zq[j][v][m], s);
@@ -947,7 +952,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                         for (int r = 0; r < ez; ++r) {
                             T* dst = ocur_of(j) + (long long)(r - S.row0_z - z) * S.osz;
                             T old[VEC];
-                            gld<T, VEC>(dst, old, nv[MID ? 0 : j], L.scalar_io);
+                            gld<T, VEC>(dst, old, vf[MID ? 0 : j], nv[MID ? 0 : j], L.scalar_io);
 #pragma unroll
                             for (int v = 0; v < VEC; ++v) {
                                 T s = fma_t(S.bw[2][0][r][0], gl[v], T(0));
@@ -955,7 +960,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                                 for (int kk = 1; kk < TB; ++kk) s = fma_t(S.bw[2][0][r][kk], zq[j][v][kk - 1], s);
                                 old[v] = L.axpy ? fma_t((T)L.dt, s, old[v]) : old[v] + s;
                             }
-                            gst<T, VEC>(dst, old, nv[MID ? 0 : j], L.scalar_io);
+                            gst<T, VEC>(dst, old, vf[MID ? 0 : j], nv[MID ? 0 : j], L.scalar_io);
                         }
                     }
                 }
@@ -970,10 +975,10 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                         for (int v = 0; v < VEC; ++v) {
                             T s = T(0);
                             if (S.padded[2]) {              // pre-padded input: the ghost plane is the array's last plane
-                                s = __ldg(u + (long long)(gx[j] + v + S.in_off_x) + (long long)(gy[j] + S.in_off_y) * S.isy +
+                                s = __ldg(u + (long long)(max(gx[j] + v, 0) + S.in_off_x) + (long long)(gy[j] + S.in_off_y) * S.isy +
                                           (long long)(S.nglob_z + 1) * S.isz);
                             } else if (S.per_face[2]) {
-                                const long long face = (long long)(gx[j] + v) + (long long)nx * gy[j];
+                                const long long face = (long long)min(max(gx[j] + v, 0), nx - 1) + (long long)nx * gy[j];
                                 const int K = S.K_r[2];
                                 const T* a = S.pf_a_r[2] + face * K;
 #pragma unroll
@@ -1001,11 +1006,11 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                                 T prev[VEC];
 #pragma unroll
                                 for (int v = 0; v < VEC; ++v) prev[v] = T(0);
-                                if (L.accumulate) gld<T, VEC>(dst, prev, nv[MID ? 0 : j], L.scalar_io);
+                                if (L.accumulate) gld<T, VEC>(dst, prev, vf[MID ? 0 : j], nv[MID ? 0 : j], L.scalar_io);
 #pragma unroll
                                 for (int v = 0; v < VEC; ++v) out[v] = fma_t(L.axpy ? (T)L.dt : T(1), out[v], prev[v]);
                             }
-                            gst<T, VEC>(dst, out, nv[MID ? 0 : j], L.scalar_io);
+                            gst<T, VEC>(dst, out, vf[MID ? 0 : j], nv[MID ? 0 : j], L.scalar_io);
                         }
                     }
                 }
@@ -1059,7 +1064,7 @@ int32_t launch_variant2(const StarConfig& C, const void* u, void* du, long long 
         attr_device = dev;
     }
     const long long len = z1 - z0;
-    const long long tiles_x = (S.nx + G::TX - 1) / G::TX;
+    const long long tiles_x = (S.nx + C.xshift + G::TX - 1) / G::TX;
     const long long tiles = tiles_x * (MID ? (S.ny + G::TY - 1) / G::TY : 1);
     // Chunking of the march axis: among the chunk lengths <= zchunk_max pick the one with the shortest makespan in
     // plane-steps (one CTA per SM works through ceil(items / SMs) items, each costing its planes plus 2R priming
@@ -1113,6 +1118,7 @@ int32_t launch_variant2(const StarConfig& C, const void* u, void* du, long long 
     // memory system: the CTAs drift further apart and the halo rows / columns neighbouring tiles share fall out of L2
     // before the second reader arrives (measured on 1024^3: 11 slots 330, 8 slots 354 Gpoints/s).
     Lp.loader = C.loader ? 1 : 0;
+    Lp.xshift = C.xshift;
     Lp.scalar_io = C.scalar_io ? 1 : 0;
     Lp.in_nx = C.in_dims[0]; Lp.in_ny = C.in_dims[1]; Lp.in_nz = C.in_dims[2];
     Lp.ns = G::NS < R + 6 ? G::NS : R + 6;

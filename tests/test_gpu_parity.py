@@ -385,7 +385,8 @@ def test_tiled_kernel_takes_prepadded_perface_and_periodic_inputs(D, O, dtype):
         nd = len(shape)
         h = tuple(1.0 / (s + 1) for s in shape)
         # --- pre-padded composite: each operator reads its own axis' ghost layer of M (the contiguous axis included: its
-        # rows are shifted by one element against du, so the kernel loads with cp.async element copies instead of TMA)
+        # rows are one element behind the rows of du, so the kernel shifts its tile origins to keep the TMA boxes aligned, or
+        # copies element-wise when the padded row pitch is not a multiple of 16 bytes)
         pairs = [make_pair("centered", 2, a, h[ax - 1], shape[ax - 1], axis=ax, dtype=dtype) for ax in range(1, nd + 1)]
         M = uniform_field([s + 2 for s in shape], dtype, seed=21)
         A = pairs[0][0]
@@ -425,6 +426,42 @@ def test_tiled_kernel_takes_prepadded_perface_and_periodic_inputs(D, O, dtype):
     G = A * D.compose(*Qd)
     assert _kernel_of(D, G, shape, shape, dtype).startswith("star"), "per-pencil BC arrays must run tiled"
     assert_close(G * u, O.apply_sum([pr[1] for pr in pairs], u, Qo), dtype, "per-pencil BC tables, 3 axes")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_prepadded_contiguous_axis_runs_on_shifted_tiles(D, O, dtype):
+    """mul!(x_temp, A, M) with M padded along the contiguous axis (derivative_operator_functions.jl:27-69,:203,:466; the shape
+    of every Gradient / Divergence / Curl input): tile origins shifted so that the boxes of M start on 16-byte boundaries, du
+    written element-wise.  Row lengths that are a multiple of the tile width (one more tile column), narrow first / last
+    tiles, 2-D strips, non-uniform grids (TABLE), overwrite=false."""
+    vec = 16 // np.dtype(dtype).itemsize
+    tx = 32 * vec
+    shapes = [((2 * tx + (0 if vec == 2 else 2), 40, 41), 4), ((2 * tx - 2, 37, 39), 2), ((3 * tx + 6, 45, 38), 6), ((tx + 2 * vec - 2, 70, 37), 4), ((40 * tx - 2, 43), 4)]
+    for shape, a in shapes:
+        assert ((shape[0] + 2) * np.dtype(dtype).itemsize) % 16 == 0       # tensor map possible: this is the shifted-tile path
+        nd = len(shape)
+        h = tuple(1.0 / (s + 1) for s in shape)
+        M = uniform_field([s + 2 for s in shape], dtype, seed=23)
+        for nonuni in (False, True):
+            pairs = [make_pair("centered", 2, a, nonuniform_dx(shape[ax - 1], h[ax - 1], dtype) if nonuni else h[ax - 1], shape[ax - 1], axis=ax, dtype=dtype)
+                     for ax in range(1, nd + 1)]
+            A = pairs[0][0]
+            for pr in pairs[1:]:
+                A = A + pr[0]
+            kern = _kernel_of(D, A, shape, M.shape, dtype)
+            assert kern == ("star-table" if nonuni else "star"), f"{shape} nonuni={nonuni}: {kern}"
+            want = O.apply_sum([pr[1] for pr in pairs], M, None)
+            du = np.zeros(shape, dtype=dtype, order="F")
+            D.mul_(du, A, M)
+            assert_close(du, want, dtype, f"pre-padded, shifted tiles {shape} nonuni={nonuni}")
+            # one operator along the contiguous axis only (a Gradient component)
+            dx1 = np.zeros(shape, dtype=dtype, order="F")
+            D.mul_(dx1, pairs[0][0], M)
+            assert_close(dx1, O.apply_axis(pairs[0][1], M, out=np.zeros(shape, dtype=dtype, order="F")), dtype, f"pre-padded x operator {shape} nonuni={nonuni}")
+        base = uniform_field(shape, dtype, seed=24)
+        acc = D.DeviceArray.from_host(base)
+        D.mul_(acc, A, D.DeviceArray.from_host(M), overwrite=False)
+        assert np.abs(acc.to_host().astype(np.float64) - (base.astype(np.float64) + want)).max() <= TOL[np.dtype(dtype)] * np.abs(want).max()
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
