@@ -298,38 +298,40 @@ bool star_take_halo_timeout() {
     return false;
 }
 
-// Shifted tile origins (input padded along the contiguous axis, see star_configure): tiles start at x = tile * TX - xshift
-// with xshift = 1 (mod the vector length), so that every box of u starts on a 16-byte boundary.  Among those shifts take
-// the one with the fewest tile columns whose first and last tile both keep at least a boundary stencil's width of columns
-// inside the array (a row length that is a multiple of TX needs one more tile column whatever the shift).
-static void choose_xshift(const deo_plan* plan, StarConfig& cfg, bool mid) {
-    if (cfg.xshift == 0) return;
-    const int VEC = (int)(16 / plan->elem());
-    const int nwy = cfg.v2 ? 16 : cfg.nwy, py = cfg.v2 ? 2 : cfg.py;
-    const long long TX = mid ? 32 * VEC : 32 * VEC * nwy * py, nx = plan->dims[0];
-    const long long wmin = 2 * cfg.R + 2;
-    long long best = -1, best_tiles = 0;
-    for (long long sh = 1; sh < TX; sh += VEC) {
-        const long long tiles = (nx + sh + TX - 1) / TX, wlast = (nx - 1 + sh) % TX + 1, wfirst = tiles > 1 ? TX - sh : nx;
-        if (wlast < wmin || wfirst < wmin) continue;
-        if (best < 0 || tiles < best_tiles) { best = sh; best_tiles = tiles; }
-    }
-    cfg.xshift = best > 0 ? (int)best : 1;                   // no admissible shift: tile_fits rejects the plan
+// What a face tile must hold (persistent kernel): the rows next to a face are evaluated from ONE tile's shared-memory plane,
+// so the first / last tile along x (y) needs the boundary stencil's 2R+1 points and the BC's stencil inside the tile plus
+// its halo, and must own the R rows next to the face.  w = columns (rows) of the tile inside the array, halo = HX (R).
+static bool face_tile_ok(long long w, int halo, int R, int K) {
+    return w + halo >= 2 * R + 1 && w + halo >= K && w >= R;
 }
 
-// The tile geometry must contain everything the x / y edge paths read (boundary stencils and BC stencils).
-static bool tile_fits(const deo_plan* plan, const StarConfig& cfg, bool mid) {
+// Tile origins (persistent kernel): (tile_x * TX - xshift, tile_y * TY - yshift).  Shift 0 wherever it works.  An extent just
+// above a multiple of the tile (the 2^k + 1 grids) leaves a last tile too narrow for its face: a shift widens it at the
+// price of the first one.  An input padded along the contiguous axis needs xshift = 1 modulo the vector length (see
+// star_configure).  Among the admissible shifts: fewest tiles, then the smallest shift.  Slab plans and the first-generation
+// kernel keep shift 0.  Returns false when no shift fits (the plan then runs on the per-point kernel).
+static bool choose_shifts(const deo_plan* plan, StarConfig& cfg, bool mid) {
     const size_t es = plan->elem();
-    const int R = cfg.R;
-    const int VEC = (int)(16 / es), HXh = ((R + VEC - 1) / VEC) * VEC, TB = 2 * R + 2;
+    const int R = cfg.R, VEC = (int)(16 / es), HXh = ((R + VEC - 1) / VEC) * VEC;
     const int nwy = cfg.v2 ? 16 : cfg.nwy, py = cfg.v2 ? 2 : cfg.py;
-    const int TX = mid ? 32 * VEC : 32 * VEC * nwy * py, TY = nwy * py;
-    const long long nx = plan->dims[0], ny = mid ? plan->dims[1] : 1;
-    const int wlast = (int)((nx - 1 + cfg.xshift) % TX) + 1, hlast = (int)((ny - 1) % TY) + 1;
-    const int Kx = plan->bc[0].d.K_r, Ky = mid ? plan->bc[1].d.K_r : 0;
-    if ((cfg.mask & 1) && (wlast + HXh < TB - 1 || wlast + HXh < Kx || nx < TB)) return false;
-    if ((cfg.mask & 1) && cfg.xshift > 0 && nx > TX - cfg.xshift && TX - cfg.xshift < TB) return false;   // shifted first tile too narrow
-    if (mid && (cfg.mask & 2) && (hlast + R < TB - 1 || hlast + R < Ky || ny < TB)) return false;
+    const long long TX = mid ? 32 * VEC : 32 * VEC * nwy * py, TY = nwy * py;
+    const bool may_shift = cfg.v2 && plan->slab_axis < 0;
+    auto pick = [&](long long n, long long T, int halo, int Kl, int Kr, int res, int step, bool active, int* out) {
+        if (!active) { *out = 0; return true; }                          // no operator along this axis: no face logic, any tiling
+        long long best = -1, best_tiles = 0;
+        for (long long sh = res; sh < T; sh += step) {
+            if (sh > 0 && !may_shift) break;
+            const long long tiles = (n + sh + T - 1) / T, wlast = (n - 1 + sh) % T + 1, wfirst = tiles > 1 ? T - sh : n;
+            const bool ok = n >= 2 * R + 2 && face_tile_ok(wlast, halo, R, Kr) && (tiles == 1 ? face_tile_ok(n, halo, R, Kl) : face_tile_ok(wfirst, halo, R, Kl));
+            if (ok && (best < 0 || tiles < best_tiles)) { best = sh; best_tiles = tiles; }
+        }
+        if (best < 0) return false;
+        *out = (int)best;
+        return true;
+    };
+    if (!pick(plan->dims[0], TX, HXh, plan->bc[0].d.K_l, plan->bc[0].d.K_r, cfg.xres, VEC, (cfg.mask & 1) != 0 || cfg.xres != 0, &cfg.xshift)) return false;
+    if (mid && !pick(plan->dims[1], TY, R, plan->bc[1].d.K_l, plan->bc[1].d.K_r, 0, 1, (cfg.mask & 2) != 0, &cfg.yshift)) return false;
+    if (cfg.xshift % VEC != 0) cfg.scalar_io = true;                     // vectors of du straddle 16-byte boundaries
     return true;
 }
 
@@ -352,7 +354,7 @@ int32_t star_configure(deo_plan* plan) {
     // then read / written element-wise.  Slab plans keep the plain tensor-map path.
     const bool pitch_ok = ((size_t)plan->in_dim(0) * es) % 16 == 0;
     const bool need_loader = !pitch_ok || (plan->padded[0] && getenv("DEO_STAR2_NO_XSHIFT") != nullptr);
-    const int xshift = (plan->padded[0] && !need_loader) ? 1 : 0;
+    const int xres = (plan->padded[0] && !need_loader) ? 1 : 0;
     bool any_padded = false;
     for (int a = 0; a < nd; ++a) any_padded = any_padded || plan->padded[a];
     if ((need_loader || any_padded) && (!want_v2 || plan->slab_axis >= 0)) return DEO_OK;
@@ -363,8 +365,8 @@ int32_t star_configure(deo_plan* plan) {
     cfg->mid = mid;
     cfg->accumulate = plan->accumulate != 0;
     cfg->loader = need_loader;
-    cfg->xshift = xshift;
-    cfg->scalar_io = ((size_t)plan->dims[0] * es) % 16 != 0 || xshift != 0;   // rows (or, with shifted tiles, vectors) of du not 16-byte aligned
+    cfg->xres = xres;
+    cfg->scalar_io = ((size_t)plan->dims[0] * es) % 16 != 0;              // rows of du not 16-byte aligned (choose_shifts adds: vectors straddling)
     cfg->in_dims[0] = (int)plan->in_dim(0);
     cfg->in_dims[1] = mid ? (int)plan->in_dim(1) : 1;
     cfg->in_dims[2] = (int)plan->in_dim(nd - 1);
@@ -403,11 +405,11 @@ int32_t star_configure(deo_plan* plan) {
         cfg->R = R;
         cfg->mask = 0;
         const bool ok = plan->dtype == DEO_F64 ? fill_params_R<double>(plan, kaxis, mid, *cfg) : fill_params_R<float>(plan, kaxis, mid, *cfg);
-        if (ok) choose_xshift(plan, *cfg, mid);
+        const bool fits = ok && choose_shifts(plan, *cfg, mid);
         if (getenv("DEO_STAR_DEBUG"))
-            fprintf(stderr, "[star_configure] CONST: filled=%d tile_fits=%d R=%d mask=%d xshift=%d dims=%lld x %lld\n", (int)ok, ok ? (int)tile_fits(plan, *cfg, mid) : -1,
-                    R, cfg->mask, cfg->xshift, (long long)plan->dims[0], (long long)plan->dims[1]);
-        if (ok && tile_fits(plan, *cfg, mid)) {
+            fprintf(stderr, "[star_configure] CONST: filled=%d fits=%d R=%d mask=%d shifts=(%d, %d) dims=%lld x %lld\n", (int)ok, (int)fits, R, cfg->mask, cfg->xshift,
+                    cfg->yshift, (long long)plan->dims[0], (long long)plan->dims[1]);
+        if (fits) {
             for (const HostOp& h : plan->ops) if (h.d.axis == nd - 1) cfg->nedge_march = h.d.stencil_length / 2;
             plan->star = cfg;
             plan->kernel = "star";
@@ -447,8 +449,7 @@ int32_t star_configure(deo_plan* plan) {
     const size_t cursor0 = plan->blob_cursor;
     const bool ok = plan->dtype == DEO_F64 ? fill_params_table_R<double>(plan, axes, paxis, mid, *cfg)
                                            : fill_params_table_R<float>(plan, axes, paxis, mid, *cfg);
-    if (ok) choose_xshift(plan, *cfg, mid);
-    if (!ok || !tile_fits(plan, *cfg, mid)) { plan->blob_cursor = cursor0; return DEO_OK; }
+    if (!ok || !choose_shifts(plan, *cfg, mid)) { plan->blob_cursor = cursor0; return DEO_OK; }
     cfg->nedge_march = (cfg->mask & 4) ? R : 0;
     plan->star = cfg;
     plan->kernel = "star-table";

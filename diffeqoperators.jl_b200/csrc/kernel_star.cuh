@@ -72,7 +72,8 @@ struct StarConfig {
     int halo_expect = 0, halo_sides = 0;
     int group = -1;          // tiles per launch-order group (0: one wave; < 0: plain order) (DEO_STAR_GROUP)
     int sm_count = 0;
-    int xshift = 0;          // persistent kernel: tile origins shifted by this many elements along x (input padded along the contiguous axis)
+    int xshift = 0, yshift = 0;   // persistent kernel: tile origins shifted by this many elements (see Star2Launch)
+    int xres = 0;                 // xshift must equal this modulo the vector length (1: input padded along the contiguous axis)
     bool loader = false;     // persistent kernel: element copies by the helper warps instead of the tensor map (odd row pitch, pre-padded contiguous axis)
     bool scalar_io = false;  // persistent kernel: du rows not 16-byte aligned
     int in_dims[3] = {1, 1, 1};   // input extents in kernel-axis order (x, mid, march)

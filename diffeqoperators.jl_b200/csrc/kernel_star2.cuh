@@ -38,8 +38,10 @@ struct Star2Launch {
     unsigned long long timeout_ns;
     int stagger_ns;                  // experiment: CTA b starts b * stagger_ns late
     int pace_cycles;                 // experiment: minimum SM cycles between two plane issues of a CTA
-    int xshift;                      // tile origins along x are tile * TX - xshift: an input padded along the contiguous axis (rows one element
-                                     // behind the rows of du) then starts every TMA box on a 16-byte boundary; du is accessed element-wise
+    int xshift, yshift;              // tile origins are (tile_x * TX - xshift, tile_y * TY - yshift).  A shift widens a first / last tile that
+                                     // would be too narrow to hold a face's boundary stencil (extents just above a multiple of the tile);
+                                     // an odd xshift also puts the TMA boxes of an input padded along the contiguous axis (rows one element
+                                     // behind the rows of du) on 16-byte boundaries -- du is then accessed element-wise
     int loader;                      // 0: TMA tensor map; 1: cp.async element copies by the helper warps (any row pitch / element offset)
     int scalar_io;                   // du rows are not 16-byte aligned: element-wise global loads / stores of du
     int in_nx, in_ny, in_nz;         // input extents (loader == 1: bounds of the element copies)
@@ -213,7 +215,7 @@ __device__ __forceinline__ Star2Item star2_item(const Star2Launch& L, int it) {
     }
     Star2Item I;
     I.tx0 = (tile % L.tiles_x) * TX - L.xshift;
-    I.ty0 = MID ? (tile / L.tiles_x) * TY : 0;
+    I.ty0 = MID ? (tile / L.tiles_x) * TY - L.yshift : 0;
     I.zc0 = L.z_begin + chunk * L.zchunk;
     I.zc1 = min(I.zc0 + L.zchunk, L.z_end);
     return I;
@@ -232,7 +234,7 @@ __device__ __forceinline__ void star2_fix_x(const StarParams<T, R>& S, T* pl, in
     constexpr int TB = 2 * R + 2, HX = G::HX, PITCH = G::PITCH;
 #pragma unroll 1
     for (int rr = lane; rr < G::TY; rr += 32) {
-        if (MID && ty0 + rr >= ny) continue;
+        if (MID && (ty0 + rr >= ny || ty0 + rr < 0)) continue;
         T* rowl = pl + (MID ? (R + rr) * PITCH : 0);      // local row
         const T* row = rowl + HX - tx0;                  // row[x] = value at global x
         const int K = SIDE ? S.K_r[0] : S.K_l[0];
@@ -390,7 +392,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
                 const Star2Item I = star2_item<G::TX, G::TY, MID>(L, item);
                 const int n = I.zc1 - I.zc0 + 2 * R;
                 const bool f_xlo = has_x && I.tx0 <= 0, f_xhi = has_x && I.tx0 + G::TX >= nx;
-                const bool f_ylo = has_y && I.ty0 == 0, f_yhi = has_y && I.ty0 + G::TY >= ny;
+                const bool f_ylo = has_y && I.ty0 <= 0, f_yhi = has_y && I.ty0 + G::TY >= ny;
                 const bool face = f_xlo || f_xhi || f_ylo || f_yhi;
                 // per item: this lane's clamped source column of every 32-column chunk, and which of them lie inside the array
                 constexpr int NCH = (PITCH + 31) / 32;
@@ -558,7 +560,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
             const Star2Item I = star2_item<G::TX, G::TY, MID>(L, item);
             const int n = I.zc1 - I.zc0 + 2 * R;
             const bool f_xlo = has_x && I.tx0 <= 0, f_xhi = has_x && I.tx0 + G::TX >= nx;
-            const bool f_ylo = has_y && I.ty0 == 0, f_yhi = has_y && I.ty0 + G::TY >= ny;
+            const bool f_ylo = has_y && I.ty0 <= 0, f_yhi = has_y && I.ty0 + G::TY >= ny;
             const bool face = f_xlo || f_xhi || f_ylo || f_yhi;
 #pragma unroll 1
             for (int k = 0; k < n; ++k, ++g) {
@@ -634,12 +636,12 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
             }
             nv[MID ? 0 : j] = min(VEC, nx - gx[j]);
             vf[MID ? 0 : j] = max(0, -gx[j]);
-            live[j] = gx[j] < nx && gy[j] < ny;
+            live[j] = gx[j] < nx && gx[j] + VEC > 0 && gy[j] < ny && gy[j] >= 0;
             if (j == 0) ocur0 = du + (long long)gx[0] + (long long)gy[0] * S.osy + (long long)zc0 * S.osz;
         }
         // which of this thread's values come from the helper's evaluation (bit v: element v of the vector)
         const bool xlo_tile = has_x && tx0 <= 0, xhi_tile = has_x && tx0 + G::TX >= nx;
-        const bool ylo_tile = has_y && ty0 == 0, yhi_tile = has_y && ty0 + G::TY >= ny;
+        const bool ylo_tile = has_y && ty0 <= 0, yhi_tile = has_y && ty0 + G::TY >= ny;
         const bool xface = xlo_tile || xhi_tile, yface = ylo_tile || yhi_tile;
         int xsel[MID ? 1 : PY], xoff[MID ? 1 : PY], ysel[PY];  // 3-D: the PY rows of a thread share x
 #pragma unroll
@@ -680,7 +682,7 @@ k_star2(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StarPa
             }
             if constexpr (has_y) {
                 for (int i = threadIdx.x; i < G::TY * NQ; i += NW * 32)
-                    wbuf[i] = __ldg(S.tab[1] + (long long)min(ty0 + i / NQ, ny - 1) * NQ + i % NQ);
+                    wbuf[i] = __ldg(S.tab[1] + (long long)min(max(ty0 + i / NQ, 0), ny - 1) * NQ + i % NQ);
             }
             if constexpr (has_z) {
                 for (int i = threadIdx.x; i < (zc1 - zc0) * NQ; i += NW * 32)
@@ -1065,7 +1067,7 @@ int32_t launch_variant2(const StarConfig& C, const void* u, void* du, long long 
     }
     const long long len = z1 - z0;
     const long long tiles_x = (S.nx + C.xshift + G::TX - 1) / G::TX;
-    const long long tiles = tiles_x * (MID ? (S.ny + G::TY - 1) / G::TY : 1);
+    const long long tiles = tiles_x * (MID ? (S.ny + C.yshift + G::TY - 1) / G::TY : 1);
     // Chunking of the march axis: among the chunk lengths <= zchunk_max pick the one with the shortest makespan in
     // plane-steps (one CTA per SM works through ceil(items / SMs) items, each costing its planes plus 2R priming
     // planes); never cut a face's one-sided rows.
@@ -1118,7 +1120,7 @@ int32_t launch_variant2(const StarConfig& C, const void* u, void* du, long long 
     // memory system: the CTAs drift further apart and the halo rows / columns neighbouring tiles share fall out of L2
     // before the second reader arrives (measured on 1024^3: 11 slots 330, 8 slots 354 Gpoints/s).
     Lp.loader = C.loader ? 1 : 0;
-    Lp.xshift = C.xshift;
+    Lp.xshift = C.xshift; Lp.yshift = MID ? C.yshift : 0;
     Lp.scalar_io = C.scalar_io ? 1 : 0;
     Lp.in_nx = C.in_dims[0]; Lp.in_ny = C.in_dims[1]; Lp.in_nz = C.in_dims[2];
     Lp.ns = G::NS < R + 6 ? G::NS : R + 6;

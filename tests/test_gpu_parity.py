@@ -465,6 +465,40 @@ def test_prepadded_contiguous_axis_runs_on_shifted_tiles(D, O, dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+def test_extents_just_above_a_tile_multiple_run_tiled(D, O, dtype):
+    """Extents of the form k * tile + 1, + 2 (the 2^k + 1 grids): the last tile along x / y alone is too narrow to hold its
+    face's boundary stencil; the kernel shifts its tile origins instead of falling back to the per-point kernel.  Even and
+    odd row lengths (TMA / cp.async loader), Robin and Dirichlet faces, non-uniform grids, overwrite=false."""
+    vec = 16 // np.dtype(dtype).itemsize
+    tx, ty = 32 * vec, 32
+    cases = [((2 * tx + 2, 2 * ty + 1, 41), 4), ((tx + 1, ty + 2, 39), 4), ((3 * tx + 2, 3 * ty + 3, 38), 6), ((2 * tx + 1, 70, 40), 2),
+             ((32 * vec * 32 + 2, 45), 4), ((32 * vec * 32 + 1, 41), 6)]
+    for shape, a in cases:
+        nd = len(shape)
+        h = tuple(1.0 / (s + 1) for s in shape)
+        u = uniform_field(shape, dtype, seed=31)
+        for bc, nonuni in (("robin", False), ("dirichlet0", False), ("robin", True)):
+            dxs = [nonuniform_dx(shape[ax], h[ax], dtype) if nonuni else h[ax] for ax in range(nd)]
+            pairs = [make_pair("centered", 2, a, dxs[ax - 1], shape[ax - 1], axis=ax, dtype=dtype) for ax in range(1, nd + 1)]
+            A = pairs[0][0]
+            for pr in pairs[1:]:
+                A = A + pr[0]
+            if bc == "dirichlet0":
+                Q = D.compose(*D.Dirichlet0BC(dtype, shape))
+                bcs = {ax + 1: O.Dirichlet0BC(dtype) for ax in range(nd)}
+            else:
+                Q = D.compose(*D.RobinBC((1.0, 0.5, 0.25), (1.0, -0.5, 0.75), dxs if nonuni else h, 1, shape, dtype=dtype))
+                bcs = {ax + 1: O.RobinBC((1.0, 0.5, 0.25), (1.0, -0.5, 0.75), dxs[ax], 1, dtype) for ax in range(nd)}
+            G = A * Q
+            assert _kernel_of(D, G, shape, shape, dtype).startswith("star"), f"{shape} {bc} nonuni={nonuni} must run tiled"
+            want = O.apply_sum([pr[1] for pr in pairs], u, bcs)
+            assert_close(G * u, want, dtype, f"shifted tiles {shape} {bc} nonuni={nonuni}")
+        acc = D.DeviceArray.from_host(u)
+        D.mul_(acc, G, D.DeviceArray.from_host(u), overwrite=False)
+        assert np.abs(acc.to_host().astype(np.float64) - (u.astype(np.float64) + want)).max() <= TOL[np.dtype(dtype)] * np.abs(want).max()
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_tiled_kernel_takes_any_row_length(D, O, dtype):
     """Row lengths that are not a multiple of 16 bytes (no tensor map possible): cp.async element copies into the same
     shared-memory layout, element-wise stores of du.  Includes the reference's own 51^3 example
