@@ -1076,18 +1076,28 @@ int32_t launch_variant2(const StarConfig& C, const void* u, void* du, long long 
     if (zmax < 4 * R + 4) zmax = 4 * R + 4;
     long long zc = len;
     {
+        // every chunk length from the bound down to 4R+4 (below half the bound only while nothing fits): a chunk list is
+        // admissible when its last chunk keeps at least R+1 planes (or there is a single chunk)
         double best = 1e30;
-        const long long slots = C.sm_count;
-        for (long long nch = (len + zmax - 1) / zmax; nch <= len; ++nch) {
-            const long long c = (len + nch - 1) / nch;
-            if (c < 4 * R + 4 && nch > 1) break;
+        bool found = false;
+        const long long slots = C.sm_count, clo = 4 * R + 4;
+        for (long long c = zmax < len ? zmax : len; c >= clo || c == len; --c) {
             const long long nchunks = (len + c - 1) / c;
             const long long last = len - (nchunks - 1) * c;
-            if (nchunks > 1 && last < R + 1) continue;
-            const long long rounds = (tiles * nchunks + slots - 1) / slots;
-            const double cost = (double)rounds * (double)(c + 2 * R);
-            if (cost < best - 1e-12) { best = cost; zc = c; }
-            if (c * 2 < zmax) break;                       // do not go below half the bound
+            if (!(nchunks > 1 && last < R + 1)) {
+                if (found && c * 2 < zmax) break;              // do not go below half the bound
+                const long long rounds = (tiles * nchunks + slots - 1) / slots;
+                const double cost = (double)rounds * (double)(c + 2 * R);
+                if (cost < best - 1e-12) { best = cost; zc = c; found = true; }
+            }
+            if (c <= clo) break;
+        }
+        if (!found) {                                          // nothing at or below the bound: the shortest admissible chunk above it
+            const long long cap = TABLE ? (long long)G::TAB_ZMAX : len;
+            for (long long c = zmax + 1; c <= cap && c < len; ++c) {
+                const long long nchunks = (len + c - 1) / c;
+                if (len - (nchunks - 1) * c >= R + 1) { zc = c; break; }
+            }
         }
     }
     Star2Launch Lp{};

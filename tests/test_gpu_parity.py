@@ -499,6 +499,68 @@ def test_extents_just_above_a_tile_multiple_run_tiled(D, O, dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+def test_seeded_random_shapes_on_the_tiled_kernel(D, O, dtype):
+    """A seeded sweep over what the tiling has to get right at once: extents on both sides of tile multiples (shifted
+    origins along x and / or y, narrow first and last tiles), even and odd row lengths (TMA / cp.async loader), 2-D strips
+    and 3-D tiles, radius 1..3, uniform and non-uniform grids, an upwind term with a mixed-sign coefficient vector, affine
+    faces or a pre-padded input, overwrite=false -- every result against the oracle."""
+    rng = np.random.default_rng(20260 + np.dtype(dtype).itemsize)
+    vec = 16 // np.dtype(dtype).itemsize
+    tx, ty = 32 * vec, 32
+    ran_tiled, not_tiled = 0, []
+    for case in range(28):
+        nd = 3 if case % 4 else 2
+        near = lambda t, kmax: int(rng.integers(1, kmax + 1)) * t + int(rng.integers(-3, 4))
+        nx = max(near(tx, 3), 40) if nd == 3 else max(near(32 * vec * 32, 2), 40)
+        shape = (nx, max(near(ty, 3), 40), int(rng.integers(37, 60))) if nd == 3 else (nx, int(rng.integers(37, 80)))
+        a = int(rng.choice([2, 4, 6]))
+        nonuni = bool(rng.integers(0, 2))
+        upwind = bool(rng.integers(0, 2))
+        padded = bool(rng.integers(0, 3) == 0)
+        h = [1.0 / (s + 1) for s in shape]
+        dxs = [nonuniform_dx(shape[ax], h[ax], dtype) if nonuni else h[ax] for ax in range(nd)]
+        pairs = [make_pair("centered", 2, a, dxs[ax - 1], shape[ax - 1], axis=ax, dtype=dtype) for ax in range(1, nd + 1)]
+        if upwind:
+            c = np.sin(5 * np.pi * np.arange(1, shape[0] + 1) / shape[0]); c[::7] = 0.0
+            pairs.append(make_pair("upwind", 1, 2, dxs[0], shape[0], c, axis=1, dtype=dtype))
+        A = pairs[0][0]
+        for pr in pairs[1:]:
+            A = A + pr[0]
+        what = f"case {case}: {shape} a={a} nonuni={nonuni} upwind={upwind} padded={padded}"
+        if padded:
+            M = uniform_field([s + 2 for s in shape], dtype, seed=100 + case)
+            want = O.apply_sum([pr[1] for pr in pairs], M, None)
+            G, u_host, in_shape = A, M, M.shape
+        else:
+            kind = int(rng.integers(0, 3))
+            if kind == 0:
+                Q = D.compose(*D.Dirichlet0BC(dtype, shape)); bcs = {ax + 1: O.Dirichlet0BC(dtype) for ax in range(nd)}
+            elif kind == 1:
+                Q = D.compose(*D.RobinBC((1.0, 0.5, 0.25), (1.0, -0.5, 0.75), dxs if nonuni else tuple(h), 1, shape, dtype=dtype))
+                bcs = {ax + 1: O.RobinBC((1.0, 0.5, 0.25), (1.0, -0.5, 0.75), dxs[ax], 1, dtype) for ax in range(nd)}
+            else:
+                Q = D.compose(*D.RobinBC((1.0, 6.0, 10.0), (1.0, 6.0, 10.0), dxs if nonuni else tuple(h), 3, shape, dtype=dtype))
+                bcs = {ax + 1: O.RobinBC((1.0, 6.0, 10.0), (1.0, 6.0, 10.0), dxs[ax], 3, dtype) for ax in range(nd)}
+            u_host = uniform_field(shape, dtype, seed=100 + case)
+            want = O.apply_sum([pr[1] for pr in pairs], u_host, bcs)
+            G, in_shape = A * Q, shape
+        if _kernel_of(D, G, shape, in_shape, dtype).startswith("star"):
+            ran_tiled += 1
+        else:
+            not_tiled.append(what)
+        du = np.zeros(shape, dtype=dtype, order="F")
+        D.mul_(du, G, u_host)
+        assert_close(du, want, dtype, what)
+        if case % 3 == 0:
+            base = uniform_field(shape, dtype, seed=200 + case)
+            acc = D.DeviceArray.from_host(base)
+            D.mul_(acc, G, D.DeviceArray.from_host(u_host), overwrite=False)
+            err = np.abs(acc.to_host().astype(np.float64) - (base.astype(np.float64) + want)).max() / np.abs(want).max()
+            assert err <= TOL[np.dtype(dtype)], f"{what} overwrite=false: {err:.3e}"
+    assert ran_tiled >= 24, f"only {ran_tiled} of 28 cases ran on the tiled kernel; per-point kernel: {not_tiled}"
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_tiled_kernel_takes_any_row_length(D, O, dtype):
     """Row lengths that are not a multiple of 16 bytes (no tensor map possible): cp.async element copies into the same
     shared-memory layout, element-wise stores of du.  Includes the reference's own 51^3 example
