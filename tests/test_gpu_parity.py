@@ -499,6 +499,53 @@ def test_extents_just_above_a_tile_multiple_run_tiled(D, O, dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+def test_seeded_random_1d_operators(D, O, dtype):
+    """Seeded sweep of the 1-D kernels: random lengths (a few points above the smallest legal grid up to several thousand),
+    every centered / upwind family of the lists above, uniform and non-uniform grids, constant / mixed-sign coefficient
+    vectors, every BC family (PeriodicBC included) or a plain padded vector, sums of operators, overwrite=false."""
+    rng = np.random.default_rng(777 + np.dtype(dtype).itemsize)
+    for case in range(60):
+        n = int(rng.choice([rng.integers(24, 64), rng.integers(64, 700), rng.integers(700, 6000)]))
+        h = 1.0 / (n + 1)
+        nonuni = bool(rng.integers(0, 2))
+        dx = nonuniform_dx(n, h, dtype) if nonuni else h
+        nops = int(rng.integers(1, 4))
+        pairs = []
+        for _ in range(nops):
+            coeff = [1.0, -2.5, np.sin(7 * np.pi * np.arange(1, n + 1) / n)][int(rng.integers(0, 3))]
+            if rng.integers(0, 2):
+                d, a = CENTERED[int(rng.integers(0, len(CENTERED) - 2))]            # reach <= 4 and the (4,10) / (8,8) giants separately below
+                pairs.append(make_pair("centered", d, a, dx, n, coeff, dtype=dtype))
+            else:
+                d, a, off = UPWIND[int(rng.integers(0, len(UPWIND)))]
+                pairs.append(make_pair("upwind", d, a, dx, n, coeff, offside=off, dtype=dtype))
+        A = pairs[0][0]
+        for pr in pairs[1:]:
+            A = A + pr[0]
+        what = f"case {case}: n={n} nonuni={nonuni} ops={[type(p[0]).__name__ for p in pairs]}"
+        if rng.integers(0, 4) == 0:
+            x = uniform_field(n + 2, dtype, seed=300 + case)                           # plain padded vector
+            want = O.apply_axis(pairs[0][1], x)
+            for pr in pairs[1:]:
+                want = want + O.apply_axis(pr[1], x)
+            assert_close(A * x, want, dtype, what + " padded")
+            continue
+        bspec = BCS[int(rng.integers(0, len(BCS)))]
+        Qd, Qo = bc_pair(bspec, dx if (nonuni and bspec[0] in ("robin", "neumann", "general")) else h, dtype)
+        u = uniform_field(n, dtype, seed=300 + case)
+        want = O.apply_axis(pairs[0][1], u, Qo)
+        for pr in pairs[1:]:
+            want = want + O.apply_axis(pr[1], u, Qo)
+        assert_close((A * Qd) * u, want, dtype, what + f" {bspec[0]}")
+        if case % 4 == 0:
+            base = uniform_field(n, dtype, seed=400 + case)
+            acc = D.DeviceArray.from_host(base)
+            D.mul_(acc, A * Qd, D.DeviceArray.from_host(u), overwrite=False)
+            err = np.abs(acc.to_host().astype(np.float64) - (base.astype(np.float64) + want)).max() / max(np.abs(want).max(), 1e-300)
+            assert err <= TOL[np.dtype(dtype)], f"{what} overwrite=false: {err:.3e}"
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_seeded_random_shapes_on_the_tiled_kernel(D, O, dtype):
     """A seeded sweep over what the tiling has to get right at once: extents on both sides of tile multiples (shifted
     origins along x and / or y, narrow first and last tiles), even and odd row lengths (TMA / cp.async loader), 2-D strips
