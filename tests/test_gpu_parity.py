@@ -428,6 +428,47 @@ def test_tiled_kernel_takes_prepadded_perface_and_periodic_inputs(D, O, dtype):
     assert_close(G * u, O.apply_sum([pr[1] for pr in pairs], u, Qo), dtype, "per-pencil BC tables, 3 axes")
 
 
+def _per_pencil_bcs(D, O, shape, h, dtype, rng):
+    """One RobinBC per boundary pencil on every axis (different data and stencil length per pencil): product MultiDimBC list and
+    the oracle's per-face tables."""
+    Qd, Qo = [], {}
+    for ax in range(1, len(shape) + 1):
+        face = tuple(s for i, s in enumerate(shape) if i != ax - 1)
+        arr = np.empty(face, dtype=object)
+        a_l = np.zeros(face + (3,), dtype=dtype); a_r = np.zeros(face + (3,), dtype=dtype)
+        b_l = np.zeros(face, dtype=dtype); b_r = np.zeros(face, dtype=dtype)
+        for idx in np.ndindex(*face):
+            order = int(rng.integers(1, 4))
+            q = D.RobinBC(tuple(rng.uniform(0.5, 2.0, 3)), tuple(rng.uniform(0.5, 2.0, 3)), h[ax - 1], order, dtype=dtype)
+            arr[idx] = q
+            a_l[idx][:order] = q.a_l; a_r[idx][3 - order:] = q.a_r; b_l[idx] = q.b_l; b_r[idx] = q.b_r
+        Qd.append(D.MultiDimBC[ax](arr))
+        nface = int(np.prod(face))
+        Qo[ax] = O.BC(a_l.reshape((nface, 3), order="F"), b_l.reshape(-1, order="F"), a_r.reshape((nface, 3), order="F"),
+                      b_r.reshape(-1, order="F"), dtype)
+    return Qd, Qo
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_per_pencil_bc_tables_on_shifted_tiles(D, O, dtype):
+    """Per-pencil MultiDimBC arrays (multi_dim_bc_operators.jl:54-57) on extents just above tile multiples: the face index
+    of a pencil must not depend on where the tile origins are; also odd row lengths (cp.async loader) and 2-D strips."""
+    rng = np.random.default_rng(5)
+    vec = 16 // np.dtype(dtype).itemsize
+    tx, ty = 32 * vec, 32
+    for shape, a in [((tx + 2, ty + 1, 38), 4), ((2 * tx + 1, 2 * ty + 2, 40), 2), ((tx - 2 * vec, 70, 37), 6), ((32 * vec * 32 + 2, 41), 4)]:
+        h = tuple(1.0 / (s + 1) for s in shape)
+        u = uniform_field(shape, dtype, seed=25)
+        Qd, Qo = _per_pencil_bcs(D, O, shape, h, dtype, rng)
+        pairs = [make_pair("centered", 2, a, h[ax - 1], shape[ax - 1], axis=ax, dtype=dtype) for ax in range(1, len(shape) + 1)]
+        A = pairs[0][0]
+        for pr in pairs[1:]:
+            A = A + pr[0]
+        G = A * D.compose(*Qd)
+        assert _kernel_of(D, G, shape, shape, dtype).startswith("star"), f"{shape}: per-pencil BC arrays must run tiled"
+        assert_close(G * u, O.apply_sum([pr[1] for pr in pairs], u, Qo), dtype, f"per-pencil BC tables {shape}")
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_prepadded_contiguous_axis_runs_on_shifted_tiles(D, O, dtype):
     """mul!(x_temp, A, M) with M padded along the contiguous axis (derivative_operator_functions.jl:27-69,:203,:466; the shape
