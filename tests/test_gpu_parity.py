@@ -705,7 +705,7 @@ def test_overwrite_false_accumulates(D, O):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("shape,a", [((96, 70, 41), 4), ((200, 37, 30), 6), ((300, 75), 4)])
+@pytest.mark.parametrize("shape,a", [((96, 70, 41), 4), ((200, 37, 30), 6), ((300, 75), 4), ((130, 65, 40), 4), ((257, 66, 38), 2), ((4098, 45), 4)])
 def test_tiled_accumulate_and_fused_axpy(D, O, dtype, shape, a):
     """overwrite = false (convolutions.jl:17-22) and the fused explicit-stepper update u + dt*(A u)
     (3D_laplacian.jl:20-24) on the tiled kernels: every face, every march-axis edge row."""
