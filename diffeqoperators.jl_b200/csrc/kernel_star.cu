@@ -308,14 +308,14 @@ static bool face_tile_ok(long long w, int halo, int R, int K) {
 // Tile origins (persistent kernel): (tile_x * TX - xshift, tile_y * TY - yshift).  Shift 0 wherever it works.  An extent just
 // above a multiple of the tile (the 2^k + 1 grids) leaves a last tile too narrow for its face: a shift widens it at the
 // price of the first one.  An input padded along the contiguous axis needs xshift = 1 modulo the vector length (see
-// star_configure).  Among the admissible shifts: fewest tiles, then the smallest shift.  Slab plans and the first-generation
-// kernel keep shift 0.  Returns false when no shift fits (the plan then runs on the per-point kernel).
+// star_configure).  Among the admissible shifts: fewest tiles, then the smallest shift.  The first-generation kernel keeps
+// shift 0.  Returns false when no shift fits (the plan then runs on the per-point kernel).
 static bool choose_shifts(const deo_plan* plan, StarConfig& cfg, bool mid) {
     const size_t es = plan->elem();
     const int R = cfg.R, VEC = (int)(16 / es), HXh = ((R + VEC - 1) / VEC) * VEC;
     const int nwy = cfg.v2 ? 16 : cfg.nwy, py = cfg.v2 ? 2 : cfg.py;
     const long long TX = mid ? 32 * VEC : 32 * VEC * nwy * py, TY = nwy * py;
-    const bool may_shift = cfg.v2 && plan->slab_axis < 0;
+    const bool may_shift = cfg.v2;                                   // the first-generation kernel lays its tiles out from the origin only
     auto pick = [&](long long n, long long T, int halo, int Kl, int Kr, int res, int step, bool active, int* out) {
         if (!active) { *out = 0; return true; }                          // no operator along this axis: no face logic, any tiling
         long long best = -1, best_tiles = 0;
