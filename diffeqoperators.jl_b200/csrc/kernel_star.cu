@@ -351,13 +351,15 @@ int32_t star_configure(deo_plan* plan) {
     // along the contiguous axis has its rows ONE element behind the rows of du, and a TMA box must start on a 16-byte
     // boundary (an odd Float64 start index is an illegal instruction): the tile origins are shifted by one element instead
     // (tiles start at x = -1), which puts every box of u on a boundary and leaves the vectors of du misaligned -- du is
-    // then read / written element-wise.  Slab plans keep the plain tensor-map path.
+    // then read / written element-wise.  Slab plans take every path but the pre-padded ones (odd row lengths: loader, three-launch
+    // schedule).
     const bool pitch_ok = ((size_t)plan->in_dim(0) * es) % 16 == 0;
     const bool need_loader = !pitch_ok || (plan->padded[0] && getenv("DEO_STAR2_NO_XSHIFT") != nullptr);
     const int xres = (plan->padded[0] && !need_loader) ? 1 : 0;
     bool any_padded = false;
     for (int a = 0; a < nd; ++a) any_padded = any_padded || plan->padded[a];
-    if ((need_loader || any_padded) && (!want_v2 || plan->slab_axis >= 0)) return DEO_OK;
+    if (need_loader && !want_v2) return DEO_OK;
+    if (any_padded && (!want_v2 || plan->slab_axis >= 0)) return DEO_OK;   // a slab's input carries its halo planes, never a ghost layer
     const bool mid = nd == 3;
     const int kaxis[3] = {0, mid ? 1 : 2, mid ? 2 : -1};                 // plan axis -> kernel axis (x, mid, march)
     const int paxis[3] = {0, mid ? 1 : -1, mid ? 2 : 1};                 // kernel axis -> plan axis

@@ -18,7 +18,8 @@ ROBIN = ((1.0, 0.5, 0.25), (1.0, -0.5, 0.75))
 fails = 0
 for name, shape, a, dtype, reps in [("fused-launch", (256, 192, 160 * world), 4, np.float64, 3), ("three-launch (thin slabs)", (128, 96, 40 * world), 4, np.float64, 2),
                                     ("fused f32 a=6", (256, 128, 144 * world), 6, np.float32, 2), ("table (upwind + nonuniform)", (128, 96, 150 * world), 4, np.float64, 2),
-                                    ("shifted tiles (2^k + 1 extents)", (130, 65, 160 * world), 4, np.float64, 2)]:
+                                    ("shifted tiles (2^k + 1 extents)", (130, 65, 160 * world), 4, np.float64, 2),
+                                    ("odd row length (cp.async loader)", (129, 66, 120 * world), 4, np.float64, 2)]:
     h = tuple(1.0 / (s + 1) for s in shape)
     u = np.asfortranarray(np.random.default_rng(5).uniform(-1, 1, shape).astype(dtype))
     if name.startswith("table"):
