@@ -298,39 +298,25 @@ bool star_take_halo_timeout() {
     return false;
 }
 
-// What a face tile must hold (persistent kernel): the rows next to a face are evaluated from ONE tile's shared-memory plane,
-// so the first / last tile along x (y) needs the boundary stencil's 2R+1 points and the BC's stencil inside the tile plus
-// its halo, and must own the R rows next to the face.  w = columns (rows) of the tile inside the array, halo = HX (R).
-static bool face_tile_ok(long long w, int halo, int R, int K) {
-    return w + halo >= 2 * R + 1 && w + halo >= K && w >= R;
-}
-
-// Tile origins (persistent kernel): (tile_x * TX - xshift, tile_y * TY - yshift).  Shift 0 wherever it works.  An extent just
-// above a multiple of the tile (the 2^k + 1 grids) leaves a last tile too narrow for its face: a shift widens it at the
-// price of the first one.  An input padded along the contiguous axis needs xshift = 1 modulo the vector length (see
-// star_configure).  Among the admissible shifts: fewest tiles, then the smallest shift.  The first-generation kernel keeps
-// shift 0.  Returns false when no shift fits (the plan then runs on the per-point kernel).
+// Tile origins (persistent kernel): (tile_x * TX - xshift, tile_y * TY - yshift), see tiling_host.hpp.  The first-generation
+// kernel lays its tiles out from the origin only.  Returns false when no shift fits (the plan then runs on the per-point kernel).
 static bool choose_shifts(const deo_plan* plan, StarConfig& cfg, bool mid) {
     const size_t es = plan->elem();
     const int R = cfg.R, VEC = (int)(16 / es), HXh = ((R + VEC - 1) / VEC) * VEC;
     const int nwy = cfg.v2 ? 16 : cfg.nwy, py = cfg.v2 ? 2 : cfg.py;
     const long long TX = mid ? 32 * VEC : 32 * VEC * nwy * py, TY = nwy * py;
-    const bool may_shift = cfg.v2;                                   // the first-generation kernel lays its tiles out from the origin only
-    auto pick = [&](long long n, long long T, int halo, int Kl, int Kr, int res, int step, bool active, int* out) {
-        if (!active) { *out = 0; return true; }                          // no operator along this axis: no face logic, any tiling
-        long long best = -1, best_tiles = 0;
-        for (long long sh = res; sh < T; sh += step) {
-            if (sh > 0 && !may_shift) break;
-            const long long tiles = (n + sh + T - 1) / T, wlast = (n - 1 + sh) % T + 1, wfirst = tiles > 1 ? T - sh : n;
-            const bool ok = n >= 2 * R + 2 && face_tile_ok(wlast, halo, R, Kr) && (tiles == 1 ? face_tile_ok(n, halo, R, Kl) : face_tile_ok(wfirst, halo, R, Kl));
-            if (ok && (best < 0 || tiles < best_tiles)) { best = sh; best_tiles = tiles; }
-        }
-        if (best < 0) return false;
-        *out = (int)best;
-        return true;
-    };
-    if (!pick(plan->dims[0], TX, HXh, plan->bc[0].d.K_l, plan->bc[0].d.K_r, cfg.xres, VEC, (cfg.mask & 1) != 0 || cfg.xres != 0, &cfg.xshift)) return false;
-    if (mid && !pick(plan->dims[1], TY, R, plan->bc[1].d.K_l, plan->bc[1].d.K_r, 0, 1, (cfg.mask & 2) != 0, &cfg.yshift)) return false;
+    const bool may_shift = cfg.v2;
+    cfg.xshift = cfg.yshift = 0;
+    if ((cfg.mask & 1) != 0 || cfg.xres != 0) {                          // an axis without operator has no face logic: any tiling
+        const long long sh = tiling::pick_shift(plan->dims[0], TX, HXh, R, plan->bc[0].d.K_l, plan->bc[0].d.K_r, cfg.xres, VEC, may_shift);
+        if (sh < 0) return false;
+        cfg.xshift = (int)sh;
+    }
+    if (mid && (cfg.mask & 2) != 0) {
+        const long long sh = tiling::pick_shift(plan->dims[1], TY, R, R, plan->bc[1].d.K_l, plan->bc[1].d.K_r, 0, 1, may_shift);
+        if (sh < 0) return false;
+        cfg.yshift = (int)sh;
+    }
     if (cfg.xshift % VEC != 0) cfg.scalar_io = true;                     // vectors of du straddle 16-byte boundaries
     return true;
 }

@@ -19,6 +19,7 @@
 // A.ops order, w = (c*w) pre-multiplied as the reference forms it (convolutions.jl:47).
 #pragma once
 #include "kernel_star.cuh"
+#include "tiling_host.hpp"
 
 // TABLE variants on 3-D tiles: x-axis weights of a thread's own points in registers up to this radius, in shared memory
 // above it (the register queue of the larger radii leaves no room)
@@ -1068,38 +1069,9 @@ int32_t launch_variant2(const StarConfig& C, const void* u, void* du, long long 
     const long long len = z1 - z0;
     const long long tiles_x = (S.nx + C.xshift + G::TX - 1) / G::TX;
     const long long tiles = tiles_x * (MID ? (S.ny + C.yshift + G::TY - 1) / G::TY : 1);
-    // Chunking of the march axis: among the chunk lengths <= zchunk_max pick the one with the shortest makespan in
-    // plane-steps (one CTA per SM works through ceil(items / SMs) items, each costing its planes plus 2R priming
-    // planes); never cut a face's one-sided rows.
-    long long zmax = C.zchunk_max > 0 ? C.zchunk_max : len;
-    if (TABLE && zmax > G::TAB_ZMAX) zmax = G::TAB_ZMAX;
-    if (zmax < 4 * R + 4) zmax = 4 * R + 4;
-    long long zc = len;
-    {
-        // every chunk length from the bound down to 4R+4 (below half the bound only while nothing fits): a chunk list is
-        // admissible when its last chunk keeps at least R+1 planes (or there is a single chunk)
-        double best = 1e30;
-        bool found = false;
-        const long long slots = C.sm_count, clo = 4 * R + 4;
-        for (long long c = zmax < len ? zmax : len; c >= clo || c == len; --c) {
-            const long long nchunks = (len + c - 1) / c;
-            const long long last = len - (nchunks - 1) * c;
-            if (!(nchunks > 1 && last < R + 1)) {
-                if (found && c * 2 < zmax) break;              // do not go below half the bound
-                const long long rounds = (tiles * nchunks + slots - 1) / slots;
-                const double cost = (double)rounds * (double)(c + 2 * R);
-                if (cost < best - 1e-12) { best = cost; zc = c; found = true; }
-            }
-            if (c <= clo) break;
-        }
-        if (!found) {                                          // nothing at or below the bound: the shortest admissible chunk above it
-            const long long cap = TABLE ? (long long)G::TAB_ZMAX : len;
-            for (long long c = zmax + 1; c <= cap && c < len; ++c) {
-                const long long nchunks = (len + c - 1) / c;
-                if (len - (nchunks - 1) * c >= R + 1) { zc = c; break; }
-            }
-        }
-    }
+    // Chunking of the march axis (tiling_host.hpp): shortest makespan among the chunk lengths <= zchunk_max; the TABLE variants
+    // stage at most TAB_ZMAX rows of march-axis weights per item.
+    const long long zc = tiling::pick_chunk(len, C.zchunk_max, R, tiles, C.sm_count, TABLE ? (long long)G::TAB_ZMAX : 0);
     Star2Launch Lp{};
     Lp.z_begin = (int)z0; Lp.z_end = (int)z1; Lp.zchunk = (int)zc;
     Lp.nchunks = (int)((len + zc - 1) / zc);
