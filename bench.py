@@ -175,21 +175,46 @@ def ncu_traffic(name):
         return None
 
 
+def global_shape_of(args, N):
+    """-> (global extents, workload description) of this run: BASELINE's workload, `--nz` override, weak scaling along dim 3."""
+    shape, _, _, desc = WORKLOADS[args.workload]
+    gshape = tuple(shape)
+    if args.nz > 0:
+        gshape = gshape[:-1] + (args.nz,)
+        desc += f" [last extent overridden to {args.nz}]"
+    if args.scaling == "weak" and N > 1:
+        gshape = gshape[:-1] + (gshape[-1] * N,)
+    return gshape, desc
+
+
+def config_of(args, N, gshape, desc, es):
+    """The `config` object of the JSON line: what is computed, not how -- identical for this repository's arm and for the
+    reference arm of the same command line."""
+    total_bytes = float(np.prod(gshape)) * es
+    return {"workload": desc if args.scaling == "strong" or N == 1 else desc + f" (weak: {'x'.join(map(str, gshape))} global)",
+            "global_shape": list(gshape), "parallelism": f"slab{N}" if N > 1 else "single",
+            "l2": "input (>= 8 GB) far exceeds the 126 MB L2; no flush needed" if total_bytes > 1e9 else "working set may be L2-resident",
+            "values": "iid Uniform(-1,1), seeded per plane"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     name = args.workload
     dtype = WORKLOADS[name][2]
+    N = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    gshape, desc = global_shape_of(args, N)
     nthreads = os.cpu_count() or 1
     gpts, ms, sample = time_oracle(name, dtype, max(1, args.steps), min(args.warmup, 1), nthreads)
     line = {
         "impl": "reference", "metric": "stencil Gpoints/s (mul!, Float64)", "value": gpts, "unit": "Gpoints/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": args.scaling, "vs_baseline": None, "dtype": "f64" if dtype == np.float64 else "f32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[name][3], "note": "reference CPU path = C restatement of DiffEqOperators.jl's mul! (oracle/), "
-                   "Julia is not installed on the box; timed on a bounded sample with all host threads"},
-        "cpu_baseline": {"value": gpts, "unit": "Gpoints/s", "cores": nthreads, "kind": "port", "sample": sample},
+        "config": config_of(args, N, gshape, desc, np.dtype(dtype).itemsize),
+        "cpu_baseline": {"value": gpts, "unit": "Gpoints/s", "cores": nthreads, "kind": "port", "sample": sample,
+                         "note": "reference CPU path = C restatement of DiffEqOperators.jl's mul! (oracle/), Julia is not installed on the box; "
+                                 "timed on a bounded sample of the workload with all host threads, rank 0 only"},
         "e2e": {"value": gpts, "unit": "Gpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -353,15 +378,10 @@ def main():
         return float(t.item())
 
     name = args.workload
-    shape, _, dtype, desc = WORKLOADS[name]
+    shape, _, dtype, _ = WORKLOADS[name]
     if N > 1 and len(shape) != 3:
         raise SystemExit("multi-GPU runs use a 3-D workload (slabs along dim 3)")
-    gshape = tuple(shape)
-    if args.nz > 0:
-        gshape = gshape[:-1] + (args.nz,)
-        desc += f" [last extent overridden to {args.nz}]"
-    if args.scaling == "weak" and N > 1:
-        gshape = gshape[:-1] + (gshape[-1] * N,)
+    gshape, desc = global_shape_of(args, N)
     es = np.dtype(dtype).itemsize
     flags = _lib.DEO_FLAG_FORCE_GENERIC if args.force_generic else 0
     G = build_operator(D, name, gshape, dtype)
@@ -488,10 +508,7 @@ def main():
             "value": value, "unit": "Gpoints/s", "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64" if dtype == np.float64 else "f32", "data": "synthetic",
-            "config": {"workload": desc if args.scaling == "strong" or N == 1 else desc + f" (weak: {'x'.join(map(str, gshape))} global)",
-                       "global_shape": list(gshape), "parallelism": f"slab{N}" if N > 1 else "single", "kernel": kernel_name,
-                       "l2": "input (>= 8 GB) far exceeds the 126 MB L2; no flush needed" if total_pts * es > 1e9 else "working set may be L2-resident",
-                       "values": "iid Uniform(-1,1), seeded per plane"},
+            "config": config_of(args, N, gshape, desc, es), "kernel": kernel_name,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         }
         if parity is not None:
