@@ -400,10 +400,15 @@ def materialize_padded(P: BoundaryPadded):
         other = tuple(slice(1, -1) if (d + 1 in axes) else slice(None) for d in range(nd) if d != ax - 1)
         lo = np.zeros(um.shape[1:], dtype=u.dtype)
         hi = np.zeros(um.shape[1:], dtype=u.dtype)
+        # The reference swaps the periodic ghosts (lower = u[1], upper = u[end]) only in the methods specialised on an array
+        # whose element type is PeriodicBC itself (multi_dim_bc_operators.jl:221-228, :244-252).  A per-pencil array that
+        # mixes PeriodicBC with other atomic BCs goes through the generic slice_rmul (:27-52), pencil by pencil, with the
+        # 1-D rule lower = u[end], upper = u[1] (bc_operators.jl:192; test/DerivativeOperators/multi_dim_bc_test.jl:29-31).
+        all_periodic = isinstance(bcs, PeriodicBC) or (isinstance(bcs, np.ndarray) and all(isinstance(q, PeriodicBC) for q in bcs.reshape(-1)))
         for idx in np.ndindex(*um.shape[1:]):
             bc = bcs if isinstance(bcs, AtomicBC) else bcs[idx]
-            if isinstance(bc, PeriodicBC):
-                lo[idx], hi[idx] = um[(0,) + idx], um[(-1,) + idx]      # N-D periodic: lower=u[1], upper=u[end] (:221-228)
+            if all_periodic:
+                lo[idx], hi[idx] = um[(0,) + idx], um[(-1,) + idx]
             else:
                 lo[idx], hi[idx] = _ghosts_1d(bc, um[(slice(None),) + idx])
         om[(0,) + other] = lo

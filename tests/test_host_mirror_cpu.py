@@ -118,3 +118,68 @@ def test_host_side_padded_array_matches_the_reference_rules(D):
     Qc = D.compose(*D.Dirichlet0BC(np.float64, A.shape))
     PA = materialize_padded(Qc * A)
     assert PA.shape == (7, 8) and PA[0, 0] == 0 and PA[-1, -1] == 0 and np.array_equal(PA[1:-1, 1:-1], A)
+
+
+def test_multi_dim_bc_extension_follows_the_reference_test(D):
+    """test/DerivativeOperators/multi_dim_bc_test.jl:9-35, :41-88, :91-108: MultiDimBC arrays that mix RobinBC and PeriodicBC
+    pencils extend every pencil exactly as the atomic BC extends the vector (generic slice_rmul: the 1-D periodic rule),
+    Dirichlet0 along the third axis, and compose(Q1..QN) * A equals the per-axis extensions for 2..6 dimensions."""
+    from deo_b200.apply import materialize_padded
+    rng = np.random.default_rng(7373)
+    q1 = D.RobinBC((1.0, 2.0, 3.0), (0.0, -1.0, 2.0), 0.1, 4)
+    q2 = D.PeriodicBC(np.float64)
+
+    def mixed(face):
+        arr = np.empty(face, dtype=object)
+        first = face[0] // 2
+        for idx in np.ndindex(*face):
+            arr[idx] = q1 if idx[0] < first else q2
+        return arr
+
+    # 2-D
+    n, m = 8, 15
+    A = rng.random((n, m))
+    BCx, BCy = mixed((m,)), mixed((n,))
+    Ax = materialize_padded(D.MultiDimBC[1](BCx) * A)
+    Ay = materialize_padded(D.MultiDimBC[2](BCy) * A)
+    assert Ax.shape == (n + 2, m) and Ay.shape == (n, m + 2)
+    for j in range(m):
+        assert np.array_equal(Ax[:, j], materialize_padded(BCx[j] * A[:, j]))
+    for i in range(n):
+        assert np.array_equal(Ay[i, :], materialize_padded(BCy[i] * A[i, :]))
+    # 3-D
+    n, m, o = 8, 11, 12
+    A = rng.random((n, m, o))
+    BCx, BCy = mixed((m, o)), mixed((n, o))
+    Qz = D.MultiDimBC[3](D.Dirichlet0BC(np.float64), A.shape)
+    Ax = materialize_padded(D.MultiDimBC[1](BCx) * A)
+    Ay = materialize_padded(D.MultiDimBC[2](BCy) * A)
+    Az = materialize_padded(Qz * A)
+    assert Ax.shape == (n + 2, m, o) and Ay.shape == (n, m + 2, o) and Az.shape == (n, m, o + 2)
+    for j in range(m):
+        for k in range(o):
+            assert np.array_equal(Ax[:, j, k], materialize_padded(BCx[j, k] * A[:, j, k]))
+    for i in range(n):
+        for k in range(o):
+            assert np.array_equal(Ay[i, :, k], materialize_padded(BCy[i, k] * A[i, :, k]))
+    z0 = D.Dirichlet0BC(np.float64)
+    for i in range(n):
+        for j in range(m):
+            assert np.array_equal(Az[i, j, :], materialize_padded(z0 * A[i, j, :]))
+    # an array whose every pencil is periodic is the reference's specialised method: ghosts swapped (:221-228)
+    allp = np.empty((m, o), dtype=object)
+    for idx in np.ndindex(m, o):
+        allp[idx] = q2
+    Ap = materialize_padded(D.MultiDimBC[1](allp) * A)
+    assert np.array_equal(Ap[0], A[0]) and np.array_equal(Ap[-1], A[-1])
+    # compositions to higher dimension
+    for N in range(2, 7):
+        sizes = tuple(int(v) for v in rng.integers(4, 8, N))
+        A = rng.random(sizes)
+        Q1_N = D.RobinBC(tuple(rng.random(3)), tuple(rng.random(3)), [0.1] * N, 4, sizes)
+        full = materialize_padded(D.compose(*Q1_N) * A)
+        assert full.shape == tuple(s + 2 for s in sizes)
+        for d, Qd in enumerate(Q1_N):
+            one = materialize_padded(Qd * A)                    # padded along axis d only
+            sel = tuple(slice(None) if e == d else slice(1, -1) for e in range(N))
+            assert np.array_equal(full[sel], one)

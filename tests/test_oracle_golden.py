@@ -241,3 +241,54 @@ def test_nd_nonsymmetric_stencils_and_coefficients_equal_matrix_times_pencils():
             want = np.moveaxis(np.tensordot(A, np.moveaxis(M, axis - 1, 0), axes=(1, 0)), 0, axis - 1)
             assert got.shape == tuple(s - 2 if d == axis - 1 else s for d, s in enumerate(shape))
             np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-9)
+
+
+def test_regular_operator_validation():
+    """test/DerivativeOperators/regular_operator_validation.jl:3-17: derivative orders 1..6 and approximation orders 2..10 of
+    sin(x) on 200 points; the reference's own assertion is isapprox(...; atol = 1.0^(1 - aor)) = a 2-norm of the error of at
+    most 1 (kept literally), and the interior rows have to be accurate to the truncation order as well."""
+    from oracle import oracle as O
+    nx = 200
+    x = np.linspace(0, 2 * np.pi, nx)
+    dx = x[1] - x[0]
+    y = np.sin(x)
+    dy = [np.cos(x), -np.sin(x), -np.cos(x), y, np.cos(x), -np.sin(x)]
+    for dor in range(1, 7):
+        for aor in range(2, 11, 2):
+            D1 = O.CenteredDifference(dor, aor, dx, nx - 2)
+            dyt = O.apply_axis(D1, y)
+            err = dyt - dy[dor - 1][1:-1]
+            assert np.linalg.norm(err) <= 1.0, (dor, aor, np.linalg.norm(err))
+            r = D1.stencil_length // 2 + 1
+            assert np.abs(err[r:-r]).max() <= 20 * dx ** aor + 1e-15 / dx ** dor * 2e3, (dor, aor, np.abs(err[r:-r]).max())
+
+
+def test_generic_operator_validation():
+    """test/DerivativeOperators/generic_operator_validation.jl:3-60: the irregular-grid constructor fed a regular grid
+    differentiates sin(2x) to atol 10^(1-aor) (2-norm), and on a genuinely irregular grid to the reference's tolerance
+    2 * 10^(2-aor) * max(dx)^(2-dor)."""
+    from oracle import oracle as O
+    x = np.arange(0.0, np.pi, 0.01)
+    dxv = np.diff(x)
+    y = np.sin(2 * x)
+    x_, y_ = x[1:-1], y[1:-1]
+    dy = [2 * np.cos(2 * x_), -4 * np.sin(2 * x_), -8 * np.cos(2 * x_), 16 * y_, 32 * np.cos(2 * x_)]
+    for dor in range(1, 5):
+        for aor in range(2, 7):
+            D1 = O.CenteredDifference(dor, aor, dxv, len(x) - 2)
+            assert np.linalg.norm(O.apply_axis(D1, y) - dy[dor - 1]) <= 10.0 ** (1 - aor), (dor, aor)
+            # ... and its rows equal the regular-grid operator's (sparse(Dr) ~ sparse(Dir), :11-19)
+            if aor % 2 == 0:
+                Dr = O.CenteredDifference(dor, aor, dxv[0], len(x) - 2)
+                np.testing.assert_allclose(O.apply_axis(D1, y), O.apply_axis(Dr, y), rtol=0, atol=1e-6 * np.abs(dy[dor - 1]).max() / dxv[0] ** 0)
+    x = np.cumsum(np.sin(np.arange(0.0, np.pi, 0.05)))
+    x = x / x[-1] * np.pi
+    dxv = np.diff(x)
+    y = np.sin(2 * x)
+    x_, y_ = x[1:-1], y[1:-1]
+    dy = [2 * np.cos(2 * x_), -4 * np.sin(2 * x_), -8 * np.cos(2 * x_), 16 * y_, 32 * np.cos(2 * x_)]
+    for dor in range(1, 5):
+        for aor in range(4, 11):
+            D1 = O.CenteredDifference(dor, aor, dxv, len(x) - 2)
+            tol = 2 * 10.0 ** (2 - aor) * dxv.max() ** (2 - dor)
+            assert np.linalg.norm(O.apply_axis(D1, y) - dy[dor - 1]) <= tol, (dor, aor, tol)
