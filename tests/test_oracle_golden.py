@@ -292,3 +292,40 @@ def test_generic_operator_validation():
             D1 = O.CenteredDifference(dor, aor, dxv, len(x) - 2)
             tol = 2 * 10.0 ** (2 - aor) * dxv.max() ** (2 - dor)
             assert np.linalg.norm(O.apply_axis(D1, y) - dy[dor - 1]) <= tol, (dor, aor, tol)
+
+
+def test_heat_equation_with_dirichlet_and_neumann_bcs():
+    """test/DerivativeOperators/heat_eqn.jl:4-30, :32-66: du/dt = A*bc*u integrated over [0, 1] with an explicit 5th-order
+    Runge-Kutta pair (the reference uses Tsit5; scipy's RK45 here) keeps the end values (Dirichlet, rtol 0.05) and the end
+    slopes (Neumann, atol 0.1); the (2,1) upwind operator with one offside point behaves like the centered one."""
+    from scipy.integrate import solve_ivp
+    from oracle import oracle as O
+    times = np.arange(0.0, 1.01, 0.1)
+    # Dirichlet
+    h = 2 * np.pi / 511
+    x = -np.pi + h * np.arange(512)
+    ua = lambda z: -(z - 0.5) ** 2 + 1 / 12
+    u0 = ua(x)
+    bc = O.DirichletBC(ua(-np.pi - h), ua(np.pi + h))
+    for A in (O.CenteredDifference(2, 2, h, 512), O.UpwindDifference(2, 1, h, 512, 1, offside=1)):
+        sol = solve_ivp(lambda t, u: O.apply_axis(A, u, bc), (0.0, 1.0), u0, method="RK45", rtol=1e-3, atol=1e-6, dense_output=True)
+        assert sol.status == 0
+        for t in times:
+            s = sol.sol(t)
+            assert abs(s[0] - u0[0]) <= 0.05 * abs(u0[0]) and abs(s[-1] - u0[-1]) <= 0.05 * abs(u0[-1]), t
+    # Neumann
+    N = 128
+    dx = 2 * np.pi / (N - 1)
+    x = -np.pi + dx * np.arange(N)
+    u0 = ua(x)
+    c0 = np.array([-11 / 6, 3.0, -3 / 2, 1 / 3]) / dx
+    c1 = -c0[::-1]
+    for B, A in ((O.CenteredDifference(1, 2, dx, N - 2), O.CenteredDifference(2, 2, dx, N)),
+                 (O.UpwindDifference(1, 2, dx, N - 2, 1, offside=1), O.UpwindDifference(2, 1, dx, N, 1, offside=1))):
+        d = O.apply_axis(B, u0)
+        bcn = O.NeumannBC((d[0], d[-1]), dx, 1)
+        sol = solve_ivp(lambda t, u: O.apply_axis(A, u, bcn), (0.0, 1.0), u0, method="RK45", rtol=1e-3, atol=1e-6, dense_output=True)
+        assert sol.status == 0
+        for t in times:
+            s = sol.sol(t)
+            assert abs(c0 @ s[:4] - d[0]) <= 1e-1 and abs(c1 @ s[-4:] - d[-1]) <= 1e-1, t
