@@ -329,3 +329,33 @@ def test_heat_equation_with_dirichlet_and_neumann_bcs():
         for t in times:
             s = sol.sol(t)
             assert abs(c0 @ s[:4] - d[0]) <= 1e-1 and abs(c1 @ s[-4:] - d[-1]) <= 1e-1, t
+
+
+def test_fornberg_weights_against_the_reference_stencil_literals():
+    """Literal interior stencils held by the reference's tests (derivative_operators_interface.jl:146-227: "Correctness of
+    Uniform Stencils, Complete", "... Complete Half", "... Uniform Upwind Stencils"), each the Fornberg weights of the point set
+    its constructor passes to calculate_weights (derivative_operator.jl:337-339 half-offset x0 = 0.5, :655-658 upwind):
+    pins fornberg.jl:7-62 in the oracle and in the host mirror beyond the operator matrices."""
+    import deo_b200 as D
+    from oracle import oracle as O
+    cases = []
+    centered = {2: ([-0.5, 0, 0.5], [1.0, -2.0, 1.0], [-1 / 2, 1.0, 0.0, -1.0, 1 / 2]),
+                4: ([1 / 12, -2 / 3, 0, 2 / 3, -1 / 12], [-1 / 12, 4 / 3, -5 / 2, 4 / 3, -1 / 12], [1 / 8, -1.0, 13 / 8, 0.0, -13 / 8, 1.0, -1 / 8])}
+    for a, ws in centered.items():
+        for d, w in enumerate(ws, start=1):
+            sl = d + a - 1 + (d + a) % 2
+            cases.append((d, 0.0, np.arange(-(sl // 2), sl // 2 + 1, dtype=float), w))
+    half = {2: ([0.5, 0.5], [-1.0, 1.0]), 4: ([-1 / 16, 9 / 16, 9 / 16, -1 / 16], [1 / 24, -9 / 8, 9 / 8, -1 / 24])}
+    for a, ws in half.items():
+        for d, w in enumerate(ws):
+            sl = a + 2 * (d // 2) + a % 2
+            end = sl // 2
+            cases.append((d, 0.5, np.arange(1 - end, end + 1, dtype=float), w))
+    upwind = {1: ([-1.0, 1.0], [-1.0, 3.0, -3.0, 1.0]), 2: ([-3 / 2, 2.0, -1 / 2], [-5 / 2, 9.0, -12.0, 7.0, -3 / 2])}
+    for a, ws in upwind.items():
+        for d, w in zip((1, 3), ws):
+            cases.append((d, 0.0, np.arange(0.0, d + a), w))
+    assert len(cases) == 14
+    for d, x0, x, want in cases:
+        for got in (O.calculate_weights(d, x0, x), D.calculate_weights(d, x0, x)):
+            np.testing.assert_allclose(np.asarray(got, dtype=float), want, rtol=0, atol=1e-10, err_msg=f"d={d} x0={x0} x={x}")
