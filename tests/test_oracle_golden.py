@@ -359,3 +359,31 @@ def test_fornberg_weights_against_the_reference_stencil_literals():
     for d, x0, x, want in cases:
         for got in (O.calculate_weights(d, x0, x), D.calculate_weights(d, x0, x)):
             np.testing.assert_allclose(np.asarray(got, dtype=float), want, rtol=0, atol=1e-10, err_msg=f"d={d} x0={x0} x={x}")
+
+
+def test_operations_on_matrices():
+    """test/DerivativeOperators/derivative_operators_interface.jl:361-405: a (2,2) centered operator applied to matrices column
+    by column, uniform and non-uniform grids, against the analytic second derivatives of x^2 + y and x^2 + y^2 with the
+    reference's tolerances."""
+    from oracle import oracle as O
+    N, M = 51, 101
+    x1, y1 = np.linspace(0, 1, N), np.linspace(0, 1, M)
+    x2 = np.concatenate([x1[: N // 2] ** 0.2020, x1[(N + 1) // 2 - 1:] ** 2.015])
+    y2 = np.concatenate([y1[: M // 2] ** 1.793, y1[(M + 1) // 2 - 1:] ** 2.019])
+    for i, (xa, ya) in enumerate(((x1, y1), (x2, y2)), start=1):
+        dx, dy = (xa[1] - xa[0], ya[1] - ya[0]) if i == 1 else (np.diff(xa), np.diff(ya))
+        F = np.asfortranarray(xa[:, None] ** 2 + ya[None, :])
+        A = O.CenteredDifference(2, 2, dx, len(xa) - 2)
+        AF = O.apply_axis(A, F)
+        assert AF.shape == (len(xa) - 2, len(ya))
+        assert np.abs(AF - 2.0).max() <= 1e-9
+        if i == 2:      # (for i == 1 the reference builds B with len(yarr) rows for an input of len(yarr) rows -- a length mismatch, not reproduced)
+            B = O.CenteredDifference(2, 2, dy, len(ya) - 2)
+            BFt = O.apply_axis(B, np.asfortranarray(F.T))
+            assert np.abs(BFt).max() <= 1e-8
+            assert np.abs(O.apply_axis(A, np.asfortranarray(BFt.T))).max() <= 1e-4
+            G = np.asfortranarray(xa[:, None] ** 2 + ya[None, :] ** 2)
+            assert np.abs(O.apply_axis(A, G) - 2.0).max() <= 1e-9
+            BGt = O.apply_axis(B, np.asfortranarray(G.T))
+            assert BGt.shape == (len(ya) - 2, len(xa)) and np.abs(BGt - 2.0).max() <= 1e-8
+            assert np.abs(O.apply_axis(A, np.asfortranarray(BGt.T))).max() <= 1e-4
