@@ -8,9 +8,13 @@
  * (tests/golden/reference_kats.json, transcribed from the reference test
  * files cited there) by tests/test_oracle_golden.py.  The Julia reference
  * itself cannot be executed in this environment (no julia binary), so there
- * is no oracle/_ref build.  Not pinned by any reference test: mixed-sign
- * upwind coefficient vectors through mul!, Float32, non-separable N-D fields
- * (SURVEY.md section 8c).
+ * is no oracle/_ref build.  Beyond the golden vectors the oracle passes the
+ * reference's analytic tests transcribed in the same file (regular / generic
+ * operator validation, operations on matrices, heat equation with Dirichlet /
+ * Neumann BCs, the KdV single-soliton test: negative upwind coefficient, offside
+ * points, a five-coefficient GeneralBC).  Not pinned by any reference test:
+ * coefficient VECTORS of mixed sign through the upwind mul!, Float32 results,
+ * non-separable N-D fields.
  *
  * Build: make -C oracle      (gcc -O2 -ffp-contract=off -fopenmp)
  */

@@ -121,7 +121,8 @@ def test_host_side_padded_array_matches_the_reference_rules(D):
 
 
 def test_multi_dim_bc_extension_follows_the_reference_test(D):
-    """test/DerivativeOperators/multi_dim_bc_test.jl:9-35, :41-88, :91-108: MultiDimBC arrays that mix RobinBC and PeriodicBC
+    """test/DerivativeOperators/multi_dim_bc_test.jl:9-35, :41-88, :91-108 (commented out in the reference's runtests.jl; the rules are those of
+    multi_dim_bc_operators.jl:27-52, :212-252): MultiDimBC arrays that mix RobinBC and PeriodicBC
     pencils extend every pencil exactly as the atomic BC extends the vector (generic slice_rmul: the 1-D periodic rule),
     Dirichlet0 along the third axis, and compose(Q1..QN) * A equals the per-axis extensions for 2..6 dimensions."""
     from deo_b200.apply import materialize_padded

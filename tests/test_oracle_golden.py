@@ -387,3 +387,43 @@ def test_operations_on_matrices():
             BGt = O.apply_axis(B, np.asfortranarray(G.T))
             assert BGt.shape == (len(ya) - 2, len(xa)) and np.abs(BGt - 2.0).max() <= 1e-8
             assert np.abs(O.apply_axis(A, np.asfortranarray(BGt.T))).max() <= 1e-4
+
+
+def test_heat_equation_example_against_the_analytic_solution():
+    """test/DerivativeOperators/heat_equation.jl:11-36: du/dt = Delta*bc*u, Dirichlet0, u0 = sin(2 pi x) on 100 knots; at
+    t = 0.03 the solution equals sin(2 pi x) exp(-t (2 pi)^2) to rtol 1e-3 (the reference integrates with KenCarp4)."""
+    from scipy.integrate import solve_ivp
+    from oracle import oracle as O
+    nknots = 100
+    h = 1.0 / (nknots + 1)
+    knots = h * np.arange(1, nknots + 1)
+    ua = lambda x, t: np.sin(2 * np.pi * x) * np.exp(-t * (2 * np.pi) ** 2)
+    L = O.CenteredDifference(2, 2, h, nknots)
+    bc = O.Dirichlet0BC(np.float64)
+    sol = solve_ivp(lambda t, u: O.apply_axis(L, u, bc), (0.0, 0.03), ua(knots, 0.0), method="RK45", rtol=1e-6, atol=1e-9)
+    assert sol.status == 0
+    want = ua(knots, 0.03)
+    assert np.linalg.norm(sol.y[:, -1] - want) <= 1e-3 * max(np.linalg.norm(want), np.linalg.norm(sol.y[:, -1]))
+
+
+def test_kdv_single_soliton_advection_with_negative_upwind_coefficient():
+    """test/DerivativeOperators/KdV.jl:4-73: du = A*bc*u with A = UpwindDifference(1, 3, dx, n, -1) -- the c < 0 branch of the
+    upwind convolutions (convolutions.jl:134-139, :181-210) -- a time-dependent five-coefficient GeneralBC, plain, with one
+    offside point, and through the non-uniform constructor on a uniform grid; the travelling wave sech^2((x - t)/2)/2 is
+    reproduced to a 2-norm of 0.01 at t = 0, 0.5, ..., 5 (Tsit5 with tolerances 1e-6 in the reference; RK45 here)."""
+    from scipy.integrate import solve_ivp
+    from oracle import oracle as O
+    dx = 1.0 / 20
+    x = -10 + dx * np.arange(401)
+    phi = lambda z, t: 0.5 / np.cosh((z - t) / 2) ** 2
+    n = len(x)
+    ops = [O.UpwindDifference(1, 3, dx, n, -1.0), O.UpwindDifference(1, 3, dx, n, -1.0, offside=1),
+           O.UpwindDifference(1, 3, dx * np.ones(n + 1), n, -1.0, offside=1)]
+    for A in ops:
+        def rhs(t, u, A=A):
+            bc = O.GeneralBC([0, 1, -6 * phi(-10, t), 0, -1], [0, 1, -6 * phi(10, t), 0, -1], dx, 3)
+            return O.apply_axis(A, u, bc)
+        sol = solve_ivp(rhs, (0.0, 5.0), phi(x, 0.0), method="RK45", rtol=1e-6, atol=1e-6, dense_output=True)
+        assert sol.status == 0
+        for t in np.arange(0.0, 5.01, 0.5):
+            assert np.linalg.norm(sol.sol(t) - phi(x, t)) <= 0.01, (t, np.linalg.norm(sol.sol(t) - phi(x, t)))
