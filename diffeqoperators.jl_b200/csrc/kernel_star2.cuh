@@ -1,12 +1,12 @@
 // Persistent, warp-specialised tiled streaming kernel (second generation of kernel_star.cuh; same operand structures,
 // same arithmetic, same results bit for bit).
 //
-//   * ONE CTA per SM, persistent: 16 compute warps + 1 helper warp; the CTA walks a list of work items
-//     (x-y tile, march-axis chunk) and the helper keeps the TMA ring full ACROSS item boundaries, so there is no
-//     per-chunk pipeline fill / drain bubble and no co-resident CTA is needed to hide one.
+//   * ONE CTA per SM, persistent: 16 compute warps + a helper warpgroup (one TMA producer warp, three evaluator warps); the
+//     CTA takes work items (x-y tile, march-axis chunk) from a global queue and the producer keeps the TMA ring full ACROSS
+//     item boundaries, so there is no per-chunk pipeline fill / drain bubble and no co-resident CTA is needed to hide one.
 //   * compute warps run ONE code path for every tile: the 2.5-D register queue always rotates by renaming (the loop
 //     is unrolled 2R+1 times), there is no face code in it.  Rows whose stencil touches an x / y ghost (one-sided
-//     boundary rows, convolutions.jl:76-118, and the interior rows next to them) are evaluated by the HELPER warp
+//     boundary rows, convolutions.jl:76-118, and the interior rows next to them) are evaluated by the EVALUATOR warps
 //     straight from the shared-memory plane as soon as it has landed -- the affine ghost b + a.u[edge]
 //     (bc_operators.jl:188-191) included -- and parked in the plane's own halo cells (which hold nothing but the
 //     TMA's out-of-bounds zeros on a face tile); the owning compute lane picks the value up with one predicated
@@ -14,6 +14,10 @@
 //   * tile = 32*VEC x 32 points (Float64 64 x 32, Float32 128 x 32): 34 % halo instead of the 55 % of 64 x 16 tiles.
 //   * the march-axis faces stay with the compute warps (the register queue holds exactly the planes those rows
 //     need); only the few steps next to a march-axis face run the shifted-queue edge step.
+//   * tile origins may be shifted (Star2Launch.xshift / yshift; host side: tiling_host.hpp): extents just above a tile
+//     multiple keep a last tile wide enough for its face, and an input padded along the contiguous axis gets 16-byte
+//     aligned TMA boxes (du is then accessed element-wise).  Without a tensor map (row pitch not a multiple of 16 bytes)
+//     the four helper warps copy the planes with element-wise cp.async instead (Star2Launch.loader).
 //
 // Arithmetic: acc = fma(w[t], q[t], acc) over the taps in the reference's order (idx = 1..sl), operators summed in
 // A.ops order, w = (c*w) pre-multiplied as the reference forms it (convolutions.jl:47).
